@@ -1,0 +1,989 @@
+/*
+ * s2tc_oracle.c -- plain-C CPU restatement of the S2TC encoder hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see s2tc_oracle.h).  It is written to be read next to
+ * the upstream sources: every routine cites the upstream lines it restates
+ * ("ref:").  It deliberately has no templates, no function-pointer dispatch and
+ * no libc rand(): settings are runtime arguments and the random stream is an
+ * explicit, seekable replica of glibc's generator.
+ *
+ * Build: gcc -O2 -ffp-contract=off -fwrapv (see oracle/Makefile).  -fwrapv makes the
+ * int32 wrap of the SRGB metric (which the compiled reference exhibits, SURVEY.md
+ * A.2) defined behaviour here; the places that rely on it also use explicit
+ * uint32_t arithmetic.
+ */
+#include "s2tc_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ========================================================================== */
+/* colour metrics                                                              */
+/* ========================================================================== */
+
+/* wrapping int32 helpers: the compiled reference wraps on overflow */
+static inline int32_t wmul(int32_t a, int32_t b) { return (int32_t) ((uint32_t) a * (uint32_t) b); }
+static inline int32_t wadd(int32_t a, int32_t b) { return (int32_t) ((uint32_t) a + (uint32_t) b); }
+/* ref: s2tc_algorithm.cpp:215  SHRR(a,n) = (a + (1 << (n-1))) >> n, arithmetic shift */
+static inline int32_t shrr(int32_t a, int n) { return wadd(a, 1 << (n - 1)) >> n; }
+
+/* ref: s2tc_algorithm.cpp:285-296 */
+static int orc_srgb_luma(const signed char c[3])
+{
+	int r = c[0] * (int) c[0];
+	int g = c[1] * (int) c[1];
+	int b = c[2] * (int) c[2];
+	int y = 37 * (r * 84 + g * 72 + b * 28);
+	float root = sqrtf((float) y);
+	return (int) (root + 0.5f);
+}
+
+/* ref: s2tc_algorithm.cpp:317-354 -- every operation is a separately rounded fp32 op */
+static int orc_normalmap_dist(const signed char a[3], const signed char b[3])
+{
+	volatile float ca0, ca1, ca2, cb0, cb1, cb2, n, d0, d1, d2, acc;
+	ca0 = a[0] / 31.0f * 2 - 1;
+	ca1 = a[1] / 63.0f * 2 - 1;
+	ca2 = a[2] / 31.0f * 2 - 1;
+	cb0 = b[0] / 31.0f * 2 - 1;
+	cb1 = b[1] / 63.0f * 2 - 1;
+	cb2 = b[2] / 31.0f * 2 - 1;
+	n = ca0 * ca0 + ca1 * ca1 + ca2 * ca2;
+	if (n > 0) {
+		n = 1.0f / sqrtf(n);
+		ca0 *= n;
+		ca1 *= n;
+		ca2 *= n;
+	}
+	n = cb0 * cb0 + cb1 * cb1 + cb2 * cb2;
+	if (n > 0) {
+		n = 1.0f / sqrtf(n);
+		cb0 *= n;
+		cb1 *= n;
+		cb2 *= n;
+	}
+	d0 = cb0 - ca0;
+	d1 = cb1 - ca1;
+	d2 = cb2 - ca2;
+	acc = d0 * d0 + d1 * d1 + d2 * d2;
+	acc = 100000 * acc;
+	return (int) acc;
+}
+
+int orc_color_dist(int cd, const signed char a[3], const signed char b[3])
+{
+	int dr = a[0] - b[0], dg = a[1] - b[1], db = a[2] - b[2];
+	switch (cd) {
+	case ORC_AVG: /* ref: :217-223 */
+		return ((dr * dr) << 2) + dg * dg + ((db * db) << 2);
+	case ORC_W0AVG: /* ref: :225-232 */
+		return dr * dr + dg * dg + db * db;
+	default:
+	case ORC_WAVG: /* ref: :234-241 */
+		return ((dr * dr) << 2) + ((dg * dg) << 2) + db * db;
+	case ORC_YUV: { /* ref: :243-254 */
+		int y = dr * 60 + dg * 59 + db * 22;
+		int u = dr * 202 - y;
+		int v = db * 202 - y;
+		return ((y * y) << 1) + shrr(u * u, 3) + shrr(v * v, 4);
+	}
+	case ORC_RGB: { /* ref: :256-267 */
+		int y = dr * 42 + dg * 72 + db * 14;
+		int u = dr * 202 - y;
+		int v = db * 202 - y;
+		return ((y * y) << 1) + shrr(u * u, 3) + shrr(v * v, 4);
+	}
+	case ORC_SRGB: { /* ref: :269-283; su/sv wrap for saturated pairs */
+		int32_t qr = a[0] * (int) a[0] - b[0] * (int) b[0];
+		int32_t qg = a[1] * (int) a[1] - b[1] * (int) b[1];
+		int32_t qb = a[2] * (int) a[2] - b[2] * (int) b[2];
+		int32_t y = qr * 84 + qg * 72 + qb * 28;
+		int32_t u = qr * 409 - y;
+		int32_t v = qb * 409 - y;
+		int32_t sy = wmul(shrr(y, 3), shrr(y, 4));
+		int32_t su = wmul(shrr(u, 3), shrr(u, 4));
+		int32_t sv = wmul(shrr(v, 3), shrr(v, 4));
+		return wadd(wadd(shrr(sy, 4), shrr(su, 8)), shrr(sv, 9));
+	}
+	case ORC_SRGB_MIXED: { /* ref: :298-315 */
+		int ay = orc_srgb_luma(a), by = orc_srgb_luma(b);
+		int au = a[0] * 191 - ay, av = a[2] * 191 - ay;
+		int bu = b[0] * 191 - by, bv = b[2] * 191 - by;
+		int y = ay - by, u = au - bu, v = av - bv;
+		return ((y * y) << 3) + shrr(u * u, 1) + shrr(v * v, 2);
+	}
+	case ORC_NORMALMAP:
+		return orc_normalmap_dist(a, b);
+	}
+}
+
+/* ref: s2tc_algorithm.cpp:358-361 */
+int orc_alpha_dist(int a, int b)
+{
+	return (a - b) * (a - b);
+}
+
+/* ========================================================================== */
+/* 565 colour helpers (ref: s2tc_algorithm.cpp:50-138)                         */
+/* ========================================================================== */
+
+typedef struct { signed char v[3]; } col_t; /* r5, g6, b5 */
+
+static int col_eq(col_t a, col_t b) { return a.v[0] == b.v[0] && a.v[1] == b.v[1] && a.v[2] == b.v[2]; }
+
+/* ref: :70-81 lexicographic r,g,b */
+static int col_lt(col_t a, col_t b)
+{
+	int c;
+	for (c = 0; c < 3; ++c) {
+		signed char d = (signed char) (a.v[c] - b.v[c]);
+		if (d)
+			return d < 0;
+	}
+	return 0;
+}
+
+/* ref: :82-131  +-1 in 565 odometer order, with wrap */
+static col_t col_step(col_t c, int up)
+{
+	static const signed char top[3] = { 31, 63, 31 };
+	int ch;
+	for (ch = 2; ch >= 0; --ch) {
+		if (up ? (c.v[ch] < top[ch]) : (c.v[ch] > 0)) {
+			c.v[ch] += up ? 1 : -1;
+			return c;
+		}
+		c.v[ch] = up ? 0 : top[ch];
+	}
+	return c; /* wrapped all the way round */
+}
+
+static int col_is_max(col_t c) { return c.v[0] == 31 && c.v[1] == 63 && c.v[2] == 31; }
+
+static col_t col_at(const unsigned char *rgba, int iw, int x, int y)
+{
+	const unsigned char *p = rgba + (size_t) (x + y * iw) * 4;
+	col_t c;
+	c.v[0] = (signed char) p[0];
+	c.v[1] = (signed char) p[1];
+	c.v[2] = (signed char) p[2];
+	return c;
+}
+
+static int alpha_at(const unsigned char *rgba, int iw, int x, int y)
+{
+	return rgba[(size_t) (x + y * iw) * 4 + 3];
+}
+
+/* ========================================================================== */
+/* pair search (ref: s2tc_algorithm.cpp:363-478)                               */
+/* ========================================================================== */
+
+/* Picks the pair (i<j<m) minimising sum_k min(d[i][k], d[j][k] [, fixed rows]) with the
+ * reference's acceptance rule "bestsum < 0 || sum < bestsum" in (i,j) lexicographic order. */
+static void orc_pair_search(const int *d /* [rows][n] */, int n, int m, int nfixed, int *bi, int *bj)
+{
+	int i, j, k;
+	int bestsum = -1;
+	*bi = 0;
+	*bj = 1;
+	for (i = 0; i < m; ++i)
+		for (j = i + 1; j < m; ++j) {
+			int sum = 0;
+			for (k = 0; k < n; ++k) {
+				int v = d[i * n + k] < d[j * n + k] ? d[i * n + k] : d[j * n + k];
+				int f;
+				for (f = 0; f < nfixed; ++f)
+					if (d[(m + f) * n + k] < v)
+						v = d[(m + f) * n + k];
+				sum = wadd(sum, v);
+			}
+			if (bestsum < 0 || sum < bestsum) {
+				bestsum = sum;
+				*bi = i;
+				*bj = j;
+			}
+		}
+}
+
+/* ref: :367-414 */
+static void orc_reduce_colors(col_t *c, int n, int m, int cd)
+{
+	int *d = (int *) malloc(sizeof(int) * (size_t) m * n);
+	int i, j, bi, bj;
+	col_t keep;
+	for (i = 0; i < n; ++i) {
+		d[i * n + i] = 0;
+		for (j = i + 1; j < n; ++j) /* note argument order: lower index first (SRGB is not symmetric) */
+			d[i * n + j] = d[j * n + i] = orc_color_dist(cd, c[i].v, c[j].v);
+	}
+	for (i = n; i < m; ++i)
+		for (j = 0; j < n; ++j)
+			d[i * n + j] = orc_color_dist(cd, c[i].v, c[j].v);
+	orc_pair_search(d, n, m, 0, &bi, &bj);
+	keep = c[bi];
+	c[1] = c[bj];
+	c[0] = keep;
+	free(d);
+}
+
+/* ref: :415-478 */
+static void orc_reduce_alpha(unsigned char *a, int n, int m)
+{
+	int *d = (int *) malloc(sizeof(int) * (size_t) (m + 2) * n);
+	int i, j, bi, bj;
+	for (i = 0; i < n; ++i) {
+		d[i * n + i] = 0;
+		for (j = i + 1; j < n; ++j)
+			d[i * n + j] = d[j * n + i] = orc_alpha_dist(a[i], a[j]);
+	}
+	for (i = n; i < m; ++i)
+		for (j = 0; j < n; ++j)
+			d[i * n + j] = orc_alpha_dist(a[i], a[j]);
+	for (j = 0; j < n; ++j) {
+		d[m * n + j] = orc_alpha_dist(0, a[j]);
+		d[(m + 1) * n + j] = orc_alpha_dist(255, a[j]);
+	}
+	orc_pair_search(d, n, m, 2, &bi, &bj);
+	if (bi != 0)
+		a[0] = a[bi]; /* sequential writes: a[1] may read the just-overwritten a[0] only if bj == 0, impossible */
+	if (bj != 1)
+		a[1] = a[bj];
+	free(d);
+}
+
+/* ========================================================================== */
+/* index assignment (ref: s2tc_algorithm.cpp:582-643)                          */
+/* ========================================================================== */
+
+typedef struct { int n[2]; int s[2][3]; } acc_t; /* per index: count and channel sums */
+
+/* colour flavour: 2 bits/pixel.  Returns the unsigned score. */
+static unsigned orc_assign_color(uint32_t *idx, acc_t *acc, int cd, int have_trans,
+		const unsigned char *in, int iw, int w, int h, const col_t ref[2])
+{
+	unsigned score = 0;
+	int x, y, ch;
+	*idx = 0;
+	memset(acc, 0, sizeof(*acc));
+	for (x = 0; x < w; ++x)
+		for (y = 0; y < h; ++y) { /* column-major: fixes accumulation order only; sums commute */
+			int i = y * 4 + x;
+			col_t px;
+			int d0, d1, best;
+			if (have_trans && alpha_at(in, iw, x, y) == 0) {
+				*idx |= 3u << (2 * i);
+				continue;
+			}
+			px = col_at(in, iw, x, y);
+			d0 = orc_color_dist(cd, px.v, ref[0].v);
+			d1 = orc_color_dist(cd, px.v, ref[1].v);
+			best = d1 < d0;
+			acc->n[best]++;
+			for (ch = 0; ch < 3; ++ch)
+				acc->s[best][ch] += px.v[ch];
+			*idx |= (uint32_t) best << (2 * i);
+			score += (unsigned) (best ? d1 : d0);
+		}
+	return score;
+}
+
+/* alpha flavour: 3 bits/pixel with the fixed 0 / 255 codes 6 / 7 */
+static unsigned orc_assign_alpha(uint64_t *idx, acc_t *acc,
+		const unsigned char *in, int iw, int w, int h, const unsigned char ref[2])
+{
+	unsigned score = 0;
+	int x, y;
+	*idx = 0;
+	memset(acc, 0, sizeof(*acc));
+	for (x = 0; x < w; ++x)
+		for (y = 0; y < h; ++y) {
+			int i = y * 4 + x;
+			int a = alpha_at(in, iw, x, y);
+			int d0 = orc_alpha_dist(a, ref[0]);
+			int d1 = orc_alpha_dist(a, ref[1]);
+			int best = d1 < d0;
+			int bestdist = best ? d1 : d0;
+			int dz = orc_alpha_dist(a, 0);
+			if (dz <= bestdist) {
+				*idx |= (uint64_t) 6 << (3 * i);
+				score += (unsigned) dz;
+				continue;
+			}
+			dz = orc_alpha_dist(a, 255);
+			if (dz <= bestdist) {
+				*idx |= (uint64_t) 7 << (3 * i);
+				score += (unsigned) dz;
+				continue;
+			}
+			acc->n[best]++;
+			acc->s[best][0] += a;
+			*idx |= (uint64_t) best << (3 * i);
+			score += (unsigned) bestdist;
+		}
+	return score;
+}
+
+/* ref: :542-551  rounded mean of each non-empty cluster; returns 0 when both are empty */
+static int orc_eval_color(const acc_t *acc, col_t *c0, col_t *c1)
+{
+	static const int mask[3] = { 31, 63, 31 }; /* ref: :201-208 */
+	int ch;
+	if (!acc->n[0] && !acc->n[1])
+		return 0;
+	for (ch = 0; ch < 3; ++ch) {
+		if (acc->n[0])
+			c0->v[ch] = (signed char) ((((acc->s[0][ch] << 1) + acc->n[0]) / (acc->n[0] << 1)) & mask[ch]);
+		if (acc->n[1])
+			c1->v[ch] = (signed char) ((((acc->s[1][ch] << 1) + acc->n[1]) / (acc->n[1] << 1)) & mask[ch]);
+	}
+	return 1;
+}
+
+static int orc_eval_alpha(const acc_t *acc, unsigned char *a0, unsigned char *a1)
+{
+	if (!acc->n[0] && !acc->n[1])
+		return 0;
+	if (acc->n[0])
+		*a0 = (unsigned char) (((acc->s[0][0] << 1) + acc->n[0]) / (acc->n[0] << 1));
+	if (acc->n[1])
+		*a1 = (unsigned char) (((acc->s[1][0] << 1) + acc->n[1]) / (acc->n[1] << 1));
+	return 1;
+}
+
+/* ========================================================================== */
+/* refinement (ref: s2tc_algorithm.cpp:645-860)                                */
+/* ========================================================================== */
+
+/* ref: colour :767-860 (never :848-860, always :816-846, loop :767-814) */
+static uint32_t orc_refine_color(int refine, int cd, int have_trans,
+		const unsigned char *in, int iw, int w, int h, col_t *c0, col_t *c1)
+{
+	uint32_t idx = 0;
+	acc_t acc;
+	col_t ref[2];
+	int i;
+
+	if (refine == ORC_REFINE_NEVER) {
+		if (have_trans ? col_lt(*c1, *c0) : col_lt(*c0, *c1)) {
+			col_t t = *c0; *c0 = *c1; *c1 = t;
+		}
+		ref[0] = *c0;
+		ref[1] = *c1;
+		orc_assign_color(&idx, &acc, cd, have_trans, in, iw, w, h, ref);
+		return idx;
+	}
+
+	if (refine == ORC_REFINE_ALWAYS) {
+		ref[0] = *c0;
+		ref[1] = *c1;
+		orc_assign_color(&idx, &acc, cd, have_trans, in, iw, w, h, ref);
+		orc_eval_color(&acc, c0, c1);
+	} else { /* LOOP */
+		col_t n0 = *c0, n1 = *c1;
+		unsigned s = 0x7FFFFFFFu;
+		for (;;) {
+			uint32_t idx2;
+			unsigned s2;
+			ref[0] = n0;
+			ref[1] = n1;
+			s2 = orc_assign_color(&idx2, &acc, cd, have_trans, in, iw, w, h, ref);
+			if (s2 < s) {
+				idx = idx2;
+				s = s2;
+				*c0 = n0;
+				*c1 = n1;
+				if (!orc_eval_color(&acc, &n0, &n1))
+					break;
+			} else
+				break;
+		}
+	}
+
+	if (col_eq(*c0, *c1)) { /* ref: :796-805 / :828-837 -- every index that is not 1 becomes 0, transparent too */
+		*c1 = col_step(*c1, !col_is_max(*c0));
+		for (i = 0; i < 16; ++i)
+			if (((idx >> (2 * i)) & 3) != 1)
+				idx &= ~(3u << (2 * i));
+	}
+	if (have_trans ? col_lt(*c1, *c0) : col_lt(*c0, *c1)) { /* ref: :807-813 */
+		col_t t = *c0; *c0 = *c1; *c1 = t;
+		for (i = 0; i < 16; ++i)
+			if (!((idx >> (2 * i)) & 2))
+				idx ^= 1u << (2 * i);
+	}
+	return idx;
+}
+
+/* ref: alpha :645-765 */
+static uint64_t orc_refine_alpha(int refine, const unsigned char *in, int iw, int w, int h,
+		unsigned char *a0, unsigned char *a1)
+{
+	uint64_t idx = 0;
+	acc_t acc;
+	unsigned char ref[2];
+	int i;
+
+	if (refine == ORC_REFINE_NEVER) {
+		if (*a1 < *a0) {
+			unsigned char t = *a0; *a0 = *a1; *a1 = t;
+		}
+		ref[0] = *a0;
+		ref[1] = *a1;
+		orc_assign_alpha(&idx, &acc, in, iw, w, h, ref);
+		return idx;
+	}
+
+	if (refine == ORC_REFINE_ALWAYS) {
+		ref[0] = *a0;
+		ref[1] = *a1;
+		orc_assign_alpha(&idx, &acc, in, iw, w, h, ref);
+		orc_eval_alpha(&acc, a0, a1);
+	} else {
+		unsigned char n0 = *a0, n1 = *a1;
+		unsigned s = 0x7FFFFFFFu;
+		for (;;) {
+			uint64_t idx2;
+			unsigned s2;
+			ref[0] = n0;
+			ref[1] = n1;
+			s2 = orc_assign_alpha(&idx2, &acc, in, iw, w, h, ref);
+			if (s2 < s) {
+				idx = idx2;
+				s = s2;
+				*a0 = n0;
+				*a1 = n1;
+				if (!orc_eval_alpha(&acc, &n0, &n1))
+					break;
+			} else
+				break;
+		}
+	}
+
+	if (*a1 == *a0) { /* ref: :673-685 */
+		if (*a0 == 255)
+			--*a1;
+		else
+			++*a1;
+		for (i = 0; i < 16; ++i)
+			if (((idx >> (3 * i)) & 7) == 1)
+				idx &= ~((uint64_t) 7 << (3 * i));
+	}
+	if (*a1 < *a0) { /* ref: :687-705 */
+		unsigned char t = *a0; *a0 = *a1; *a1 = t;
+		for (i = 0; i < 16; ++i) {
+			unsigned v = (unsigned) ((idx >> (3 * i)) & 7), nv;
+			if (v == 0)
+				nv = 1;
+			else if (v == 1)
+				nv = 0;
+			else if (v >= 6)
+				nv = v;
+			else
+				nv = 7 - v;
+			idx = (idx & ~((uint64_t) 7 << (3 * i))) | ((uint64_t) nv << (3 * i));
+		}
+	}
+	return idx;
+}
+
+/* ========================================================================== */
+/* the block encoder (ref: s2tc_algorithm.cpp:872-1108, dispatch :1110-1194)   */
+/* ========================================================================== */
+
+static void put565(unsigned char *out, col_t c)
+{
+	out[0] = (unsigned char) (((c.v[1] & 0x07) << 5) | c.v[2]);
+	out[1] = (unsigned char) ((c.v[0] << 3) | (c.v[1] >> 3));
+}
+
+void orc_encode_block(unsigned char *out, const unsigned char *rgba, int iw, int w, int h,
+		int dxt, int cd, int nrandom, int refine, orc_rand_t *rng)
+{
+	int cap = 16 + (nrandom >= 0 ? nrandom : 0);
+	col_t *c;
+	unsigned char *ca;
+	int x, y, i;
+	int fast;
+
+	/* dispatch defaults: ref :1120 (refine), :1156 (dxt), :1183 (cd), :1139 (NORMALMAP never FAST) */
+	if (refine != ORC_REFINE_NEVER && refine != ORC_REFINE_LOOP)
+		refine = ORC_REFINE_ALWAYS;
+	if (dxt != ORC_DXT1 && dxt != ORC_DXT3)
+		dxt = ORC_DXT5;
+	if (cd < ORC_RGB || cd > ORC_NORMALMAP)
+		cd = ORC_WAVG;
+	fast = (nrandom < 0 && cd != ORC_NORMALMAP);
+	if (cap < 3)
+		cap = 3;
+	c = (col_t *) malloc(sizeof(col_t) * cap);
+	ca = (unsigned char *) malloc(cap);
+
+	if (fast) { /* ref: :879-935 */
+		static const signed char black[3] = { 0, 0, 0 };
+		int dmin = 0x7FFFFFFF, dmax = 0;
+		c[0].v[0] = 31; c[0].v[1] = 63; c[0].v[2] = 31;
+		c[1].v[0] = 0; c[1].v[1] = 0; c[1].v[2] = 0;
+		if (dxt == ORC_DXT5)
+			ca[0] = ca[1] = rgba[3];
+		for (x = 0; x < w; ++x)
+			for (y = 0; y < h; ++y) {
+				col_t px = col_at(rgba, iw, x, y);
+				int a = alpha_at(rgba, iw, x, y);
+				int d;
+				if (dxt == ORC_DXT1 && a == 0)
+					continue;
+				d = orc_color_dist(cd, px.v, black);
+				if (d > dmax) {
+					dmax = d;
+					c[1] = px;
+				}
+				if (d < dmin) {
+					dmin = d;
+					c[0] = px;
+				}
+				if (dxt == ORC_DXT5 && a != 255) {
+					if (a > ca[1])
+						ca[1] = (unsigned char) a;
+					if (a < ca[0])
+						ca[0] = (unsigned char) a;
+				}
+			}
+	} else { /* ref: :936-1007 */
+		int n = 0, m;
+		for (x = 0; x < w; ++x)
+			for (y = 0; y < h; ++y) {
+				c[n] = col_at(rgba, iw, x, y);
+				ca[n] = (unsigned char) alpha_at(rgba, iw, x, y);
+				if (dxt == ORC_DXT1 && ca[n] == 0)
+					continue;
+				++n;
+			}
+		if (n == 0) {
+			n = 1;
+			c[0].v[0] = c[0].v[1] = c[0].v[2] = 0;
+			ca[0] = 0;
+		}
+		m = n;
+		if (nrandom > 0) { /* ref: :962-993 */
+			col_t mins = c[0], maxs = c[0];
+			int mina = dxt == ORC_DXT5 ? ca[0] : 0, maxa = mina;
+			int len[3], lena, ch;
+			for (i = 1; i < n; ++i) {
+				for (ch = 0; ch < 3; ++ch) {
+					if (c[i].v[ch] < mins.v[ch]) mins.v[ch] = c[i].v[ch];
+					if (c[i].v[ch] > maxs.v[ch]) maxs.v[ch] = c[i].v[ch];
+				}
+				if (dxt == ORC_DXT5) {
+					if (ca[i] < mina) mina = ca[i];
+					if (ca[i] > maxa) maxa = ca[i];
+				}
+			}
+			for (ch = 0; ch < 3; ++ch)
+				len[ch] = (signed char) (maxs.v[ch] - mins.v[ch] + 1);
+			lena = dxt == ORC_DXT5 ? maxa - mina + 1 : 0;
+			for (i = 0; i < nrandom; ++i) {
+				for (ch = 0; ch < 3; ++ch)
+					c[m].v[ch] = (signed char) (mins.v[ch] + orc_rand_next(rng) % len[ch]);
+				if (dxt == ORC_DXT5)
+					ca[m] = (unsigned char) (mina + orc_rand_next(rng) % lena);
+				++m;
+			}
+		} else if (n == 1) { /* ref: :997-1001 */
+			c[1] = c[0];
+			m = n = 2;
+		}
+		orc_reduce_colors(c, n, m, cd);
+		if (dxt == ORC_DXT5)
+			orc_reduce_alpha(ca, n, m);
+	}
+
+	/* ref: :1010-1027 */
+	if (col_eq(c[0], c[1]))
+		c[1] = col_step(c[1], !col_is_max(c[0]));
+	if (dxt == ORC_DXT5 && ca[0] == ca[1]) {
+		if (ca[0] == 255)
+			--ca[1];
+		else
+			++ca[1];
+	}
+
+	/* ref: :1029-1107 */
+	{
+		uint32_t cidx = orc_refine_color(refine, cd, dxt == ORC_DXT1, rgba, iw, w, h, &c[0], &c[1]);
+		unsigned char *cout = out + (dxt == ORC_DXT1 ? 0 : 8);
+		if (dxt == ORC_DXT3) { /* ref: :862-870 */
+			uint64_t bits = 0;
+			for (x = 0; x < w; ++x)
+				for (y = 0; y < h; ++y)
+					bits |= (uint64_t) alpha_at(rgba, iw, x, y) << (4 * (y * 4 + x));
+			for (i = 0; i < 8; ++i)
+				out[i] = (unsigned char) (bits >> (8 * i));
+		} else if (dxt == ORC_DXT5) {
+			uint64_t aidx = orc_refine_alpha(refine, rgba, iw, w, h, &ca[0], &ca[1]);
+			out[0] = ca[0];
+			out[1] = ca[1];
+			for (i = 0; i < 6; ++i)
+				out[2 + i] = (unsigned char) (aidx >> (8 * i));
+		}
+		put565(cout, c[0]);
+		put565(cout + 2, c[1]);
+		for (i = 0; i < 4; ++i)
+			cout[4 + i] = (unsigned char) (cidx >> (8 * i));
+	}
+	free(c);
+	free(ca);
+}
+
+/* ========================================================================== */
+/* 565 pre-pass (ref: s2tc_algorithm.cpp:1196-1465)                            */
+/* ========================================================================== */
+
+static int imin(int a, int b) { return a < b ? a : b; }
+static int imax(int a, int b) { return a > b ? a : b; }
+
+/* ref: :1198-1207 */
+static int orc_diffuse(int *carry, int src, int shift)
+{
+	int top = (1 << (8 - shift)) - 1;
+	int s = src + *carry;
+	int q = imax(0, imin(s >> shift, top));
+	int back = (q << shift) | (q >> (8 - 2 * shift));
+	*carry = s - back;
+	return q;
+}
+
+/* ref: :1208-1216 */
+static int orc_diffuse1(int *carry, int src)
+{
+	int s = src + *carry;
+	int q = s >= 128;
+	*carry = s - (q ? 255 : 0);
+	return q;
+}
+
+/* ref: :1218-1261; shift == 7 selects the 1-bit variant (floyd1) */
+static int orc_floyd(int *thisrow, int *downrow, int src, int shift)
+{
+	int s = ((src << 4) | (src >> 4)) + thisrow[1];
+	int q, back, err, e7, e3, e5;
+	if (shift == 7) {
+		q = s >= 2048;
+		back = q ? 4095 : 0;
+	} else {
+		int top = (1 << (8 - shift)) - 1;
+		q = imax(0, imin(s >> (shift + 4), top));
+		back = q * 4095 / top;
+	}
+	err = s - back;
+	e7 = (err * 7 + 8) / 16;
+	err -= e7;
+	e3 = (err * 3 + 4) / 9;
+	err -= e3;
+	e5 = (err * 5 + 3) / 6;
+	err -= e5;
+	thisrow[2] += e7;
+	downrow[0] += e3;
+	downrow[1] += e5;
+	downrow[2] += err;
+	return q;
+}
+
+void orc_rgb565_image(unsigned char *out, const unsigned char *src, int w, int h,
+		int srccomps, int alphabits, int dither)
+{
+	size_t npix = (size_t) w * h, p;
+	int x, y;
+	if (srccomps != 3)
+		srccomps = 4; /* ref: :1455-1464 */
+	if (alphabits != 1 && alphabits != 4)
+		alphabits = 8; /* ref: :1437-1449 */
+	if (dither != ORC_DITHER_NONE && dither != ORC_DITHER_FLOYDSTEINBERG)
+		dither = ORC_DITHER_SIMPLE; /* ref: :1419-1431 */
+
+	/* alpha for 3-component sources and the 8-bit copy are common to all modes */
+	if (srccomps == 3) {
+		for (p = 0; p < npix; ++p)
+			out[p * 4 + 3] = (unsigned char) ((1 << alphabits) - 1);
+	} else if (alphabits == 8) {
+		for (p = 0; p < npix; ++p)
+			out[p * 4 + 3] = src[p * 4 + 3];
+	}
+
+	if (dither == ORC_DITHER_NONE) { /* ref: :1269-1306 */
+		for (p = 0; p < npix; ++p) {
+			out[p * 4 + 0] = src[p * srccomps + 0] >> 3;
+			out[p * 4 + 1] = src[p * srccomps + 1] >> 2;
+			out[p * 4 + 2] = src[p * srccomps + 2] >> 3;
+		}
+		if (srccomps == 4 && alphabits != 8)
+			for (p = 0; p < npix; ++p)
+				out[p * 4 + 3] = src[p * 4 + 3] >> (8 - alphabits);
+	} else if (dither == ORC_DITHER_SIMPLE) { /* ref: :1307-1349 -- carries never reset */
+		int cr = 0, cg = 0, cb = 0, cal = 0;
+		for (p = 0; p < npix; ++p) {
+			out[p * 4 + 0] = (unsigned char) orc_diffuse(&cr, src[p * srccomps + 0], 3);
+			out[p * 4 + 1] = (unsigned char) orc_diffuse(&cg, src[p * srccomps + 1], 2);
+			out[p * 4 + 2] = (unsigned char) orc_diffuse(&cb, src[p * srccomps + 2], 3);
+		}
+		if (srccomps == 4 && alphabits != 8)
+			for (p = 0; p < npix; ++p)
+				out[p * 4 + 3] = (unsigned char) (alphabits == 1
+					? orc_diffuse1(&cal, src[p * 4 + 3])
+					: orc_diffuse(&cal, src[p * 4 + 3], 8 - alphabits));
+	} else { /* ref: :1350-1412 */
+		int pw = w + 2;
+		int *rows = (int *) calloc((size_t) 6 * pw, sizeof(int));
+		for (y = 0; y < h; ++y) {
+			int *cur = rows + ((y & 1) ? 3 : 0) * pw;
+			int *nxt = rows + ((y & 1) ? 0 : 3) * pw;
+			memset(nxt, 0, sizeof(int) * 3 * (size_t) pw);
+			for (x = 0; x < w; ++x) {
+				p = (size_t) x + (size_t) y * w;
+				out[p * 4 + 0] = (unsigned char) orc_floyd(cur + x, nxt + x, src[p * srccomps + 0], 3);
+				out[p * 4 + 1] = (unsigned char) orc_floyd(cur + pw + x, nxt + pw + x, src[p * srccomps + 1], 2);
+				out[p * 4 + 2] = (unsigned char) orc_floyd(cur + 2 * pw + x, nxt + 2 * pw + x, src[p * srccomps + 2], 3);
+			}
+		}
+		if (srccomps == 4 && alphabits != 8) {
+			/* ref: :1380,1397 -- the alpha pass reuses the scratch rows WITHOUT clearing the
+			 * first "this" row, so alpha row 0 starts from whatever the RGB pass left there */
+			for (y = 0; y < h; ++y) {
+				int *cur = rows + (y & 1) * pw;
+				int *nxt = rows + (!(y & 1)) * pw;
+				memset(nxt, 0, sizeof(int) * (size_t) pw);
+				for (x = 0; x < w; ++x) {
+					p = (size_t) x + (size_t) y * w;
+					out[p * 4 + 3] = (unsigned char) orc_floyd(cur + x, nxt + x, src[p * 4 + 3],
+							alphabits == 1 ? 7 : 8 - alphabits);
+				}
+			}
+		}
+		free(rows);
+	}
+}
+
+/* ========================================================================== */
+/* image loop (ref: s2tc_libtxc_dxtn.cpp:142-299)                              */
+/* ========================================================================== */
+
+static int orc_draws_per_block(int dxt, int nrandom)
+{
+	if (nrandom <= 0)
+		return 0;
+	return nrandom * (dxt == ORC_DXT5 ? 4 : 3);
+}
+
+void orc_encode_block_rows(const unsigned char *reduced, int width, int height, int row0, int row1,
+		int dxt, int cd, int nrandom, int refine, uint64_t cursor0,
+		unsigned char *dest, int dst_row_stride)
+{
+	int bs = dxt == ORC_DXT1 ? 8 : 16;
+	int bw = (width + 3) / 4;
+	/* ref: :243,261,279 -- a stride below width*2 (DXT1) / width*4 means "tight" */
+	int tight = ((width + 3) & ~3) * (bs / 4);
+	int row_bytes = dst_row_stride >= width * (bs / 4) ? dst_row_stride : tight;
+	orc_rand_t rng;
+	int by, bx;
+	if (nrandom > 0)
+		orc_rand_seek(&rng, cursor0 + (uint64_t) row0 * bw * orc_draws_per_block(dxt, nrandom));
+	for (by = row0; by < row1; ++by) {
+		int j = by * 4;
+		int ny = height > j + 3 ? 4 : height - j;
+		unsigned char *blk = dest + (size_t) by * row_bytes;
+		for (bx = 0; bx < bw; ++bx) {
+			int i = bx * 4;
+			int nx = width > i + 3 ? 4 : width - i;
+			orc_encode_block(blk, reduced + ((size_t) j * width + i) * 4, width, nx, ny,
+					dxt, cd, nrandom, refine, &rng);
+			blk += bs;
+		}
+	}
+}
+
+int orc_compress_image(int srccomps, int width, int height, const unsigned char *src,
+		unsigned int destformat, unsigned char *dest, int dst_row_stride,
+		int dither, int cd, int nrandom, int refine, orc_rand_t *rng)
+{
+	int dxt, alphabits;
+	unsigned char *reduced;
+	uint64_t cursor = rng ? rng->draws : 0;
+	int bh = (height + 3) / 4, bw = (width + 3) / 4;
+	switch (destformat) { /* ref: :218-236 */
+	case 0x83F0:
+	case 0x83F1: dxt = ORC_DXT1; alphabits = 1; break;
+	case 0x83F2: dxt = ORC_DXT3; alphabits = 4; break;
+	case 0x83F3: dxt = ORC_DXT5; alphabits = 8; break;
+	default: return -1;
+	}
+	reduced = (unsigned char *) malloc((size_t) width * height * 4 + 4);
+	orc_rgb565_image(reduced, src, width, height, srccomps, alphabits, dither);
+	orc_encode_block_rows(reduced, width, height, 0, bh, dxt, cd, nrandom, refine, cursor, dest, dst_row_stride);
+	if (rng && nrandom > 0)
+		orc_rand_seek(rng, cursor + (uint64_t) bh * bw * orc_draws_per_block(dxt, nrandom));
+	free(reduced);
+	return 0;
+}
+
+/* ========================================================================== */
+/* S3TC -> S2TC transcode (ref: s2tc_from_s3tc.cpp:77-190)                     */
+/* ========================================================================== */
+
+#define CHECKER 0x22882288u
+
+/* colour half of a DXT3/DXT5 block: no 1-bit alpha is possible (ref: :77-111) */
+static void orc_transcode_color_opaque(unsigned char *b)
+{
+	unsigned c0 = b[0] | (b[1] << 8), c1 = b[2] | (b[3] << 8);
+	uint32_t px = b[4] | (b[5] << 8) | ((uint32_t) b[6] << 16) | ((uint32_t) b[7] << 24);
+	/* 00->00, 01->01, 1x -> 00/01 by checkerboard */
+	px = (px & ((~px & 0xAAAAAAAAu) >> 1)) | ((px & CHECKER) >> 1);
+	if (c1 >= c0) {
+		unsigned t = c0; c0 = c1; c1 = t;
+		px ^= 0x55555555u;
+	}
+	b[0] = c0 & 0xFF; b[1] = c0 >> 8; b[2] = c1 & 0xFF; b[3] = c1 >> 8;
+	b[4] = px & 0xFF; b[5] = (px >> 8) & 0xFF; b[6] = (px >> 16) & 0xFF; b[7] = (px >> 24) & 0xFF;
+}
+
+/* DXT1 block: index 3 stays transparent when c1 >= c0 (ref: :113-147) */
+static void orc_transcode_color_dxt1(unsigned char *b)
+{
+	unsigned c0 = b[0] | (b[1] << 8), c1 = b[2] | (b[3] << 8);
+	uint32_t px = b[4] | (b[5] << 8) | ((uint32_t) b[6] << 16) | ((uint32_t) b[7] << 24);
+	if (c1 >= c0) {
+		/* 00->00, 01->01, 10 -> 00/01, 11 stays */
+		px = (px & ~((~px & 0x55555555u) << 1)) | ((px & CHECKER) >> 1);
+	} else {
+		unsigned t;
+		px = (px & ((~px & 0xAAAAAAAAu) >> 1)) | ((px & CHECKER) >> 1);
+		t = c0; c0 = c1; c1 = t;
+		px ^= 0x55555555u;
+	}
+	b[0] = c0 & 0xFF; b[1] = c0 >> 8; b[2] = c1 & 0xFF; b[3] = c1 >> 8;
+	b[4] = px & 0xFF; b[5] = (px >> 8) & 0xFF; b[6] = (px >> 16) & 0xFF; b[7] = (px >> 24) & 0xFF;
+}
+
+/* alpha half of a DXT5 block (ref: :149-190) */
+static void orc_transcode_alpha_dxt5(unsigned char *b)
+{
+	const uint64_t ones = 01111111111111111ull, checker = 00101101001011010ull;
+	unsigned a0 = b[0], a1 = b[1];
+	uint64_t px = 0, sel;
+	int i;
+	for (i = 0; i < 6; ++i)
+		px |= (uint64_t) b[2 + i] << (8 * i);
+	if (a1 >= a0) {
+		sel = (px >> 1) ^ (px >> 2); /* codes 2..5 interpolate, 6/7 are the fixed 0/255 */
+		px = (px & ~((sel & ones) * 7)) | (sel & checker);
+	} else {
+		unsigned t;
+		sel = (px >> 1) | (px >> 2); /* codes 2..7 interpolate */
+		px = (px & ~((sel & ones) * 7)) | (sel & checker);
+		t = a0; a0 = a1; a1 = t;
+		px ^= ones;
+	}
+	b[0] = (unsigned char) a0;
+	b[1] = (unsigned char) a1;
+	for (i = 0; i < 6; ++i)
+		b[2 + i] = (unsigned char) (px >> (8 * i));
+}
+
+/* ref: :254-263 */
+void orc_transcode_blocks(unsigned char *blocks, size_t nblocks, int dxt)
+{
+	size_t bs = dxt == ORC_DXT1 ? 8 : 16, k;
+	for (k = 0; k < nblocks; ++k) {
+		unsigned char *b = blocks + k * bs;
+		if (dxt == ORC_DXT1)
+			orc_transcode_color_dxt1(b);
+		else
+			orc_transcode_color_opaque(b + 8);
+		if (dxt == ORC_DXT5)
+			orc_transcode_alpha_dxt5(b);
+	}
+}
+
+/* ========================================================================== */
+/* decode (ref: s2tc_libtxc_dxtn.cpp:35-140)                                   */
+/* ========================================================================== */
+
+void orc_fetch_texel(int dxt, int rgb_only, int src_row_stride, const unsigned char *pixdata,
+		int i, int j, unsigned char t[4])
+{
+	int bs = dxt == ORC_DXT1 ? 8 : 16;
+	const unsigned char *blk = pixdata + (size_t) (((src_row_stride + 3) >> 2) * (j >> 2) + (i >> 2)) * bs;
+	const unsigned char *cb = blk + (dxt == ORC_DXT1 ? 0 : 8);
+	unsigned c = cb[0] + 256u * cb[1], c1 = cb[2] + 256u * cb[3];
+	int code = (cb[4 + (j & 3)] >> (2 * (i & 3))) & 3;
+	int alpha = 255;
+	if (code == 1)
+		c = c1;
+	else if (code == 3 && dxt == ORC_DXT1 && c1 >= c) {
+		c = 0;
+		alpha = 0;
+	} else if (code >= 2) {
+		if ((i ^ j) & 1)
+			c = c1;
+	}
+	t[0] = (c >> 11) & 0x1F; t[0] = (unsigned char) ((t[0] << 3) | (t[0] >> 2));
+	t[1] = (c >> 5) & 0x3F;  t[1] = (unsigned char) ((t[1] << 2) | (t[1] >> 4));
+	t[2] = c & 0x1F;         t[2] = (unsigned char) ((t[2] << 3) | (t[2] >> 2));
+	if (dxt == ORC_DXT1) {
+		t[3] = (unsigned char) (rgb_only ? 255 : alpha);
+	} else if (dxt == ORC_DXT3) { /* ref: :96-97 */
+		int a = (blk[(j & 3) * 2 + ((i & 3) >> 1)] >> (4 * (i & 1))) & 0x0F;
+		t[3] = (unsigned char) (a | (a << 4));
+	} else { /* ref: :119-139 */
+		unsigned a = blk[0], a1 = blk[1];
+		uint64_t bits = 0;
+		int k, ab;
+		for (k = 0; k < 6; ++k)
+			bits |= (uint64_t) blk[2 + k] << (8 * k);
+		ab = (int) ((bits >> (3 * ((j & 3) * 4 + (i & 3)))) & 7);
+		if (ab == 1)
+			a = a1;
+		else if (ab == 6 && a1 >= a)
+			a = 0;
+		else if (ab >= 6 && a1 >= a) /* 7, or 6 falling through is impossible here */
+			a = 255;
+		else if (ab >= 2) {
+			if ((i ^ j) & 1)
+				a = a1;
+		}
+		t[3] = (unsigned char) a;
+	}
+}
+
+/* ========================================================================== */
+/* mip reduce (ref: s2tc_compress.c:427-493)                                   */
+/* ========================================================================== */
+
+void orc_mip_reduce(const unsigned char *in, unsigned char *out, int *width, int *height,
+		int destwidth, int destheight)
+{
+	int w = *width, h = *height, x, y, ch;
+	int halve_w = w > destwidth, halve_h = h > destheight;
+	int nw = halve_w ? w >> 1 : w, nh = halve_h ? h >> 1 : h;
+	size_t row = (size_t) w * 4;
+	if (!halve_w && !halve_h)
+		return;
+	for (y = 0; y < nh; ++y)
+		for (x = 0; x < nw; ++x) {
+			const unsigned char *p = in + (size_t) (halve_h ? 2 * y : y) * row + (size_t) (halve_w ? 2 * x : x) * 4;
+			unsigned char px[4];
+			for (ch = 0; ch < 4; ++ch) {
+				if (halve_w && halve_h)
+					px[ch] = (unsigned char) ((p[ch] + p[4 + ch] + p[row + ch] + p[row + 4 + ch]) >> 2);
+				else if (halve_w)
+					px[ch] = (unsigned char) ((p[ch] + p[4 + ch]) >> 1);
+				else
+					px[ch] = (unsigned char) ((p[ch] + p[row + ch]) >> 1);
+			}
+			/* in-place safe: the write position never passes the read position */
+			memcpy(out + ((size_t) y * nw + x) * 4, px, 4);
+		}
+	*width = nw;
+	*height = nh;
+}
