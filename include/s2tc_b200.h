@@ -1,0 +1,124 @@
+/*
+ * s2tc_b200.h -- C ABI of the B200 (sm_100a) S2TC encoder.
+ *
+ * This is the boundary a host program binds (dlopen/dlsym, cgo, JNI, ctypes ...): plain pointers,
+ * sizes and ints, no C++ or torch types.  It has two layers:
+ *
+ *  1. the reference's own entry points, re-exported unchanged so that the library is a drop-in for
+ *     libtxc_dxtn.so:   tx_compress_dxtn, fetch_2d_texel_*            -> include/txc_dxtn.h
+ *                       s2tc_encode_block_func, rgb565_image           -> include/s2tc_algorithm.h
+ *  2. the batched/device-pointer calls below (prefix s2tc_b200_), which is what those entry points
+ *     are built on and what a caller that already has texels in GPU memory should use.
+ *
+ * Every function returns 0 on success or a negative S2TC_B200_E* code; s2tc_b200_last_error() gives
+ * the text of the most recent failure on the calling thread.  There is NO CPU fallback: without a
+ * usable CUDA device the calls fail with S2TC_B200_ENODEVICE.
+ *
+ * Enumerator values are the reference's (s2tc_algorithm.h:31-63).
+ */
+#ifndef S2TC_B200_H
+#define S2TC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { S2TC_B200_DITHER_NONE = 0, S2TC_B200_DITHER_SIMPLE = 1, S2TC_B200_DITHER_FLOYDSTEINBERG = 2 };
+enum { S2TC_B200_DXT1 = 0, S2TC_B200_DXT3 = 1, S2TC_B200_DXT5 = 2 };
+enum { S2TC_B200_REFINE_NEVER = 0, S2TC_B200_REFINE_ALWAYS = 1, S2TC_B200_REFINE_LOOP = 2 };
+enum {
+	S2TC_B200_RGB = 0, S2TC_B200_YUV, S2TC_B200_SRGB, S2TC_B200_SRGB_MIXED,
+	S2TC_B200_AVG, S2TC_B200_WAVG, S2TC_B200_W0AVG, S2TC_B200_NORMALMAP
+};
+
+enum {
+	S2TC_B200_OK = 0,
+	S2TC_B200_ENODEVICE = -1, /* no CUDA device / driver, or the device is not usable */
+	S2TC_B200_EINVAL = -2,    /* bad argument (format, sizes, null pointer) */
+	S2TC_B200_ECUDA = -3,     /* a CUDA call failed; see s2tc_b200_last_error() */
+	S2TC_B200_ENOMEM = -4,
+	S2TC_B200_EUNSUPPORTED = -5 /* valid request this build cannot run on the device (stated in the message) */
+};
+
+/* Settings of one encode.  What tx_compress_dxtn reads from its arguments and from the S2TC_*
+ * environment (reference s2tc_libtxc_dxtn.cpp:156-231), made explicit. */
+typedef struct s2tc_b200_settings {
+	int dxt;     /* S2TC_B200_DXT1/3/5                       (from destformat, ref :218-231) */
+	int cd;      /* colour metric, S2TC_COLORDIST_MODE       (ref :175-197, default WAVG) */
+	int nrandom; /* S2TC_RANDOM_COLORS                       (ref :199-202, default -1 = fast mode) */
+	int refine;  /* S2TC_REFINE_COLORS                       (ref :204-216, default ALWAYS) */
+	int dither;  /* S2TC_DITHER_MODE                         (ref :161-173, default SIMPLE) */
+} s2tc_b200_settings;
+
+typedef struct s2tc_b200_ctx s2tc_b200_ctx; /* one per (thread, device); owns a stream and workspaces */
+
+const char *s2tc_b200_last_error(void);
+int s2tc_b200_device_count(void);
+
+int s2tc_b200_ctx_create(int device, s2tc_b200_ctx **out);
+void s2tc_b200_ctx_destroy(s2tc_b200_ctx *ctx);
+/* process-wide lazily created context on device S2TC_B200_DEVICE (default 0): what the
+ * handle-less reference entry points use (tx_compress_dxtn has no init/teardown) */
+s2tc_b200_ctx *s2tc_b200_default_ctx(void);
+
+/* ---- whole image, host buffers: the path behind tx_compress_dxtn ------------------------------
+ * src: width*height*srccomps bytes, tightly packed, top row first (srccomps 3 or 4; anything else is
+ * treated as 4, ref s2tc_algorithm.cpp:1455-1464).  dest/dst_row_stride as for tx_compress_dxtn
+ * (ref s2tc_libtxc_dxtn.cpp:243,261,279).  *rand_cursor (may be NULL = 0) is the number of rand() values
+ * the reference process would have consumed before this call; it is advanced by
+ * blocks * 3|4 * nrandom when nrandom > 0 (ref s2tc_algorithm.cpp:984-992).
+ * Pinned (cudaHostAlloc / cudaHostRegister) src and dest are copied without staging. */
+int s2tc_b200_compress_host(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int srccomps, int width, int height,
+		const uint8_t *src, uint8_t *dest, int dst_row_stride, uint64_t *rand_cursor);
+
+/* ---- block rows of an image already in device memory ------------------------------------------
+ * Encodes block rows [row0, row1) of a width x height image.  d_src_rows addresses texel row 4*row0;
+ * d_dst receives the blocks of those rows, tightly packed.  rand_cursor0 is the cursor of the IMAGE's
+ * first block (the row offset is added internally).  carry (4 ints r,g,b,a; may be NULL = zeros) is the
+ * DITHER_SIMPLE error carried into texel row 4*row0 and is updated to the carry leaving the range.
+ * `stream` is a cudaStream_t (NULL = the context's own stream); the call is asynchronous unless
+ * carry != NULL.  This is the sharding primitive: ranks/GPUs take disjoint row ranges. */
+int s2tc_b200_encode_rows_device(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int srccomps, int width, int height,
+		const void *d_src_rows, int row0, int row1, void *d_dst, uint64_t rand_cursor0, int *carry, void *stream);
+
+/* DITHER_SIMPLE transfer function of the texel rows of block rows [row0,row1): 4 channels x 3 words.
+ * s2tc_b200_carry_apply(map, channel, srccomps, alphabits, carry_in) evaluates one on the host, so a
+ * set of shards can resolve their incoming carries with one tiny exchange. */
+int s2tc_b200_dither_summary_device(s2tc_b200_ctx *ctx, int srccomps, int alphabits, int width, int height,
+		const void *d_src_rows, int row0, int row1, uint64_t maps[12], void *stream);
+int s2tc_b200_carry_apply(const uint64_t map[3], int channel, int srccomps, int alphabits, int carry_in);
+
+/* ---- 565 pre-pass only: backs the exported rgb565_image (ref s2tc_algorithm.h:38) ------------- */
+int s2tc_b200_rgb565_host(s2tc_b200_ctx *ctx, uint8_t *out, const uint8_t *src, int width, int height, int srccomps,
+		int alphabits, int dither);
+
+/* ---- one block: backs the function pointers s2tc_encode_block_func returns (ref s2tc_algorithm.h:65-66)
+ * rgba addresses the block's first texel inside a pre-reduced 4-byte/texel image of row stride iw. */
+int s2tc_b200_encode_block_host(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, uint8_t *out, const uint8_t *rgba, int iw,
+		int w, int h, uint64_t *rand_cursor);
+
+/* ---- S3TC -> S2TC transcode of nblocks blocks, in place (ref s2tc_from_s3tc.cpp:254-263) ------ */
+int s2tc_b200_transcode_host(s2tc_b200_ctx *ctx, int dxt, uint8_t *blocks, size_t nblocks);
+int s2tc_b200_transcode_device(s2tc_b200_ctx *ctx, int dxt, void *d_blocks, size_t nblocks, void *stream);
+
+/* ---- process-wide rand() cursor used by the handle-less entry points -------------------------- */
+uint64_t s2tc_b200_rand_cursor_get(void);
+void s2tc_b200_rand_cursor_set(uint64_t draws);
+
+/* ---- measurement helpers (bench.py): device-side timing on the context's stream ---------------- */
+int s2tc_b200_sync(s2tc_b200_ctx *ctx);
+/* number of kernel launches this context has issued so far */
+uint64_t s2tc_b200_launch_count(s2tc_b200_ctx *ctx);
+/* device milliseconds spent in each kernel family since the last reset, measured with CUDA events when
+ * profiling is enabled (s2tc_b200_profile_enable(ctx, 1)): [0] pre-pass, [1] random candidates,
+ * [2] pair search, [3] finish, [4] fast encode, [5] transcode; counts in the second array */
+int s2tc_b200_profile_enable(s2tc_b200_ctx *ctx, int on);
+int s2tc_b200_profile_read(s2tc_b200_ctx *ctx, double ms[6], uint64_t launches[6], int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

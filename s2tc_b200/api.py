@@ -1,0 +1,293 @@
+"""ctypes binding of include/s2tc_b200.h, include/s2tc_b200_txc_dxtn.h and include/s2tc_b200_algorithm.h.
+
+Names, argument meaning and error behaviour follow the reference interface: settings are the
+(DxtMode, ColorDistMode, nrandom, RefinementMode, DitherMode) tuple of s2tc_algorithm.h:31-66 and
+`tx_compress_dxtn` reads them from the S2TC_* environment on every call (s2tc_libtxc_dxtn.cpp:156-216).
+"""
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_LIBDIR = os.path.join(_HERE, "lib")
+
+# enumerators: values of the reference (s2tc_algorithm.h:31-63)
+DITHER_NONE, DITHER_SIMPLE, DITHER_FLOYDSTEINBERG = 0, 1, 2
+DXT1, DXT3, DXT5 = 0, 1, 2
+REFINE_NEVER, REFINE_ALWAYS, REFINE_LOOP = 0, 1, 2
+RGB, YUV, SRGB, SRGB_MIXED, AVG, WAVG, W0AVG, NORMALMAP = range(8)
+
+GL_FORMAT = {DXT1: 0x83F1, DXT3: 0x83F2, DXT5: 0x83F3}
+_CD_NAMES = ["RGB", "YUV", "SRGB", "SRGB_MIXED", "AVG", "WAVG", "W0AVG", "NORMALMAP"]
+_REFINE_NAMES = ["NEVER", "ALWAYS", "LOOP"]
+_DITHER_NAMES = ["NONE", "SIMPLE", "FLOYDSTEINBERG"]
+
+_u8p = C.POINTER(C.c_ubyte)
+
+
+class S2TCError(RuntimeError):
+    """A call into the CUDA library failed (code = S2TC_B200_E*)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"s2tc_b200 error {code}: {msg}")
+        self.code = code
+
+
+class _Settings(C.Structure):
+    _fields_ = [("dxt", C.c_int), ("cd", C.c_int), ("nrandom", C.c_int), ("refine", C.c_int), ("dither", C.c_int)]
+
+
+@dataclass
+class Settings:
+    """Defaults are the reference's (s2tc_libtxc_dxtn.cpp:156-159)."""
+    dxt: int = DXT1
+    cd: int = WAVG
+    nrandom: int = -1
+    refine: int = REFINE_ALWAYS
+    dither: int = DITHER_SIMPLE
+
+    def c(self):
+        return _Settings(self.dxt, self.cd, self.nrandom, self.refine, self.dither)
+
+
+def settings_from_env(dxt=DXT1, env=None):
+    """The reference's environment parsing (case-insensitive, bad values keep the default)."""
+    env = os.environ if env is None else env
+    s = Settings(dxt=dxt)
+
+    def pick(var, names, cur):
+        v = env.get(var)
+        if v is None:
+            return cur
+        for i, n in enumerate(names):
+            if v.upper() == n:
+                return i
+        return cur
+
+    s.dither = pick("S2TC_DITHER_MODE", _DITHER_NAMES, s.dither)
+    s.cd = pick("S2TC_COLORDIST_MODE", _CD_NAMES, s.cd)
+    s.refine = pick("S2TC_REFINE_COLORS", _REFINE_NAMES, s.refine)
+    if "S2TC_RANDOM_COLORS" in env:
+        s.nrandom = _atoi(env["S2TC_RANDOM_COLORS"])
+    return s
+
+
+def _atoi(v):
+    v = v.strip()
+    n = 0
+    sign = 1
+    i = 0
+    if i < len(v) and v[i] in "+-":
+        sign = -1 if v[i] == "-" else 1
+        i += 1
+    while i < len(v) and v[i].isdigit():
+        n = n * 10 + int(v[i])
+        i += 1
+    return sign * n
+
+
+def block_bytes(dxt):
+    return 8 if dxt == DXT1 else 16
+
+
+def draws_per_block(dxt, nrandom):
+    return 0 if nrandom <= 0 else nrandom * (4 if dxt == DXT5 else 3)
+
+
+def lib_path(name="libs2tc_b200.so"):
+    return os.path.join(_LIBDIR, name)
+
+
+def build(verbose=False):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", _CSRC, "-j", str(os.cpu_count() or 4), "all"], capture_output=not verbose, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building s2tc_b200/csrc failed:\n" + (r.stdout or "") + (r.stderr or ""))
+
+
+_lib = None
+
+
+def lib():
+    """The loaded shared object.  Missing library = ImportError: the encoder has no other implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise ImportError(f"{path} is missing: build it with `make -C {_CSRC}` (or s2tc_b200.build()); "
+                          "s2tc_b200 has no CPU fallback")
+    L = C.CDLL(path)
+    vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+    sp = C.POINTER(_Settings)
+    L.s2tc_b200_last_error.restype = C.c_char_p
+    L.s2tc_b200_device_count.restype = i32
+    L.s2tc_b200_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    L.s2tc_b200_ctx_destroy.argtypes = [vp]
+    L.s2tc_b200_default_ctx.restype = vp
+    L.s2tc_b200_compress_host.argtypes = [vp, sp, i32, i32, i32, vp, vp, i32, C.POINTER(u64)]
+    L.s2tc_b200_encode_rows_device.argtypes = [vp, sp, i32, i32, i32, vp, i32, i32, vp, u64, C.POINTER(i32), vp]
+    L.s2tc_b200_dither_summary_device.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, C.POINTER(u64), vp]
+    L.s2tc_b200_carry_apply.argtypes = [C.POINTER(u64), i32, i32, i32, i32]
+    L.s2tc_b200_rgb565_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32]
+    L.s2tc_b200_encode_block_host.argtypes = [vp, sp, vp, vp, i32, i32, i32, C.POINTER(u64)]
+    L.s2tc_b200_transcode_host.argtypes = [vp, i32, vp, C.c_size_t]
+    L.s2tc_b200_transcode_device.argtypes = [vp, i32, vp, C.c_size_t, vp]
+    L.s2tc_b200_rand_cursor_get.restype = u64
+    L.s2tc_b200_rand_cursor_set.argtypes = [u64]
+    L.s2tc_b200_sync.argtypes = [vp]
+    L.s2tc_b200_launch_count.argtypes = [vp]
+    L.s2tc_b200_launch_count.restype = u64
+    L.s2tc_b200_profile_enable.argtypes = [vp, i32]
+    L.s2tc_b200_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), i32]
+    L.tx_compress_dxtn.argtypes = [i32, i32, i32, vp, C.c_uint, vp, i32]
+    L.tx_compress_dxtn.restype = None
+    L.rgb565_image.argtypes = [vp, vp, i32, i32, i32, i32, i32]
+    L.rgb565_image.restype = None
+    blockfn = C.CFUNCTYPE(None, vp, vp, i32, i32, i32, i32)
+    L.s2tc_encode_block_func.argtypes = [i32, i32, i32, i32]
+    L.s2tc_encode_block_func.restype = blockfn
+    L.get_s2tc_encoder.argtypes = [i32, i32, i32, i32]
+    L.get_s2tc_encoder.restype = blockfn
+    for f in ("fetch_2d_texel_rgb_dxt1", "fetch_2d_texel_rgba_dxt1", "fetch_2d_texel_rgba_dxt3", "fetch_2d_texel_rgba_dxt5"):
+        getattr(L, f).argtypes = [i32, vp, i32, i32, vp]
+        getattr(L, f).restype = None
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise S2TCError(rc, lib().s2tc_b200_last_error().decode(errors="replace"))
+
+
+def _addr(x):
+    """Host/device address of a numpy array, torch tensor or int."""
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    raise TypeError(type(x))
+
+
+class Encoder:
+    """One encoder context on one GPU (owns a CUDA stream and its workspaces)."""
+
+    FAMILIES = ("prepass", "candidates", "search", "finish", "fast", "transcode")
+
+    def __init__(self, device=0):
+        self._ctx = C.c_void_p()
+        _check(lib().s2tc_b200_ctx_create(int(device), C.byref(self._ctx)))
+        self.device = int(device)
+
+    def close(self):
+        if self._ctx:
+            lib().s2tc_b200_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- host buffers -------------------------------------------------------------------------
+    def compress(self, img, settings, cursor=0, stride=0, out=None, return_cursor=False):
+        """img: (H, W, 3|4) uint8 numpy array (or a pinned torch CPU tensor).  Returns the encoded bytes
+        exactly as tx_compress_dxtn lays them out for dstRowStride = `stride`."""
+        h, w, comps = img.shape
+        bs = block_bytes(settings.dxt)
+        bw, bh = (w + 3) // 4, (h + 3) // 4
+        tight = bw * bs
+        row_bytes = stride if stride >= w * (bs // 4) else tight
+        nbytes = max(bh * row_bytes, 1) + (tight if stride else 0)
+        if out is None:
+            out = np.zeros(nbytes, np.uint8)
+        cur = C.c_uint64(cursor)
+        s = settings.c()
+        _check(lib().s2tc_b200_compress_host(self._ctx, C.byref(s), comps, w, h, _addr(img), _addr(out), stride,
+                                             C.byref(cur)))
+        if stride == 0 and isinstance(out, np.ndarray):
+            out = out[:bh * tight]
+        return (out, cur.value) if return_cursor else out
+
+    def rgb565_image(self, img, alphabits, dither):
+        h, w, comps = img.shape
+        out = np.zeros((h, w, 4), np.uint8)
+        _check(lib().s2tc_b200_rgb565_host(self._ctx, _addr(out), _addr(np.ascontiguousarray(img)), w, h, comps, alphabits,
+                                           dither))
+        return out
+
+    def encode_block(self, px, w, h, settings, cursor=0, iw=4):
+        """px: pre-reduced texels, row stride iw."""
+        px = np.ascontiguousarray(px, np.uint8)
+        out = np.zeros(block_bytes(settings.dxt), np.uint8)
+        cur = C.c_uint64(cursor)
+        s = settings.c()
+        _check(lib().s2tc_b200_encode_block_host(self._ctx, C.byref(s), _addr(out), _addr(px), iw, w, h, C.byref(cur)))
+        return out
+
+    def transcode(self, blocks, dxt):
+        b = np.array(blocks, np.uint8, copy=True).reshape(-1)
+        _check(lib().s2tc_b200_transcode_host(self._ctx, dxt, _addr(b), b.size // block_bytes(dxt)))
+        return b
+
+    # ---- device buffers (torch tensors or raw addresses) ----------------------------------------
+    def encode_rows_device(self, src_rows, width, height, comps, row0, row1, dst, settings, cursor0=0, carry=None,
+                           stream=None):
+        """src_rows: device buffer holding texel rows 4*row0 .. of a width x height image.
+        carry: None, or a list of 4 ints updated in place (DITHER_SIMPLE carry in/out; synchronises)."""
+        s = settings.c()
+        cptr = None
+        if carry is not None:
+            arr = (C.c_int * 4)(*carry)
+            cptr = arr
+        _check(lib().s2tc_b200_encode_rows_device(self._ctx, C.byref(s), comps, width, height, _addr(src_rows), row0, row1,
+                                                  _addr(dst), cursor0, cptr, stream))
+        if carry is not None:
+            carry[:] = list(arr)
+
+    def dither_summary_device(self, src_rows, width, height, comps, alphabits, row0, row1, stream=None):
+        maps = (C.c_uint64 * 12)()
+        _check(lib().s2tc_b200_dither_summary_device(self._ctx, comps, alphabits, width, height, _addr(src_rows), row0, row1,
+                                                     maps, stream))
+        return list(maps)
+
+    @staticmethod
+    def carry_apply(maps, comps, alphabits, carry):
+        """Carry leaving a texel range with transfer maps `maps` (12 words) for an incoming carry (4 ints)."""
+        out = []
+        for ch in range(4):
+            m = (C.c_uint64 * 3)(*maps[3 * ch:3 * ch + 3])
+            out.append(lib().s2tc_b200_carry_apply(m, ch, comps, alphabits, carry[ch]))
+        return out
+
+    def transcode_device(self, blocks, dxt, nblocks, stream=None):
+        _check(lib().s2tc_b200_transcode_device(self._ctx, dxt, _addr(blocks), nblocks, stream))
+
+    # ---- measurement ------------------------------------------------------------------------------
+    def sync(self):
+        _check(lib().s2tc_b200_sync(self._ctx))
+
+    def launch_count(self):
+        return int(lib().s2tc_b200_launch_count(self._ctx))
+
+    def profile(self, on=True):
+        _check(lib().s2tc_b200_profile_enable(self._ctx, 1 if on else 0))
+
+    def profile_read(self, reset=True):
+        ms = (C.c_double * 6)()
+        n = (C.c_uint64 * 6)()
+        _check(lib().s2tc_b200_profile_read(self._ctx, ms, n, 1 if reset else 0))
+        return {f: (ms[i], int(n[i])) for i, f in enumerate(self.FAMILIES)}
+
+
+def tx_compress_dxtn(srccomps, width, height, src, destformat, dest, dst_row_stride):
+    """The libtxc_dxtn entry point itself (reads the S2TC_* environment; errors go to stderr)."""
+    lib().tx_compress_dxtn(srccomps, width, height, _addr(src), destformat, _addr(dest), dst_row_stride)

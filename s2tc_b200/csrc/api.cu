@@ -1,0 +1,600 @@
+// api.cu -- the s2tc_b200_* C ABI (include/s2tc_b200.h): contexts, workspaces, and the orchestration of
+// the kernels in kernels_*.cu.  No encoding arithmetic happens on the host in this file: the host
+// side only sizes buffers, computes the rand() jump polynomials for a launch, and moves bytes.
+#include "../../include/s2tc_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace s2tc;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof(buf), fmt, ap);
+	va_end(ap);
+	g_last_error = buf;
+	return code;
+}
+
+#define CU(call)                                                                                           \
+	do {                                                                                                   \
+		cudaError_t e_ = (call);                                                                           \
+		if (e_ != cudaSuccess)                                                                             \
+			return fail(e_ == cudaErrorMemoryAllocation ? S2TC_B200_ENOMEM : S2TC_B200_ECUDA, "%s: %s", #call, \
+					cudaGetErrorString(e_));                                                               \
+	} while (0)
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t n)
+	{
+		if (n <= cap)
+			return cudaSuccess;
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 8 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e == cudaSuccess)
+			cap = want;
+		return e;
+	}
+	void release()
+	{
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+enum Family { kFamPrepass = 0, kFamCand, kFamSearch, kFamFinish, kFamFast, kFamTranscode, kNumFam };
+
+struct PendingTiming {
+	int fam;
+	cudaEvent_t a, b;
+};
+
+constexpr int kPlanRing = 64;
+constexpr int kBlocksPerRandThread = 32;
+constexpr long long kSlabBlocks = 1 << 20; // MODE_NORMAL works through an image in slabs of at most this many blocks
+
+} // namespace
+
+struct s2tc_b200_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	std::mutex mu;
+	DevBuf src, reduced, out, ends, cand_c, cand_a, dither_ws, plans, small;
+	RandPlan *h_plans = nullptr; // pinned ring
+	int plan_next = 0;
+	int *h_carry = nullptr; // pinned, 4 ints
+	uint64_t *h_summary = nullptr; // pinned, 12 words
+	uint8_t *h_block = nullptr;   // pinned, 64 + 16 bytes for the single-block path
+	uint64_t launches = 0;
+	bool profiling = false;
+	double fam_ms[kNumFam] = {0};
+	uint64_t fam_launches[kNumFam] = {0};
+	std::vector<PendingTiming> pending;
+};
+
+namespace {
+
+struct FamScope { // brackets a group of launches of one family with events when profiling is on
+	s2tc_b200_ctx *c;
+	cudaStream_t st;
+	int fam;
+	cudaEvent_t a = nullptr, b = nullptr;
+	FamScope(s2tc_b200_ctx *c_, cudaStream_t st_, int fam_, int nlaunch) : c(c_), st(st_), fam(fam_)
+	{
+		c->launches += nlaunch;
+		c->fam_launches[fam] += nlaunch;
+		if (c->profiling) {
+			cudaEventCreate(&a);
+			cudaEventCreate(&b);
+			cudaEventRecord(a, st);
+		}
+	}
+	~FamScope()
+	{
+		if (a) {
+			cudaEventRecord(b, st);
+			c->pending.push_back({fam, a, b});
+		}
+	}
+};
+
+int settings_normalise(const s2tc_b200_settings *in, s2tc_b200_settings &s)
+{
+	if (!in)
+		return fail(S2TC_B200_EINVAL, "settings is NULL");
+	s = *in;
+	s.dxt = norm_dxt(s.dxt);
+	s.cd = norm_cd(s.cd);
+	s.refine = norm_refine(s.refine);
+	if (s.dither != kDitherNone && s.dither != kDitherFloyd)
+		s.dither = kDitherSimple; // ref s2tc_algorithm.cpp:1419-1431
+	return 0;
+}
+
+// Encodes the blocks of `v` (a slab whose first block is block number blk0 of the image) into d_dst.
+int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &v, long long blk0, uint64_t cursor0,
+		void *d_dst, cudaStream_t st)
+{
+	const long long nblocks = (long long) v.blocks_w * v.blocks_h;
+	if (nblocks == 0)
+		return 0;
+	if (is_fast_mode(s.cd, s.nrandom)) {
+		FamScope f(c, st, kFamFast, 1);
+		CU(launch_fast_encode(s.dxt, s.cd, s.refine, v, d_dst, st));
+		return 0;
+	}
+	const int nrandom = s.nrandom > 0 ? s.nrandom : 0;
+	if (nrandom > pair_search_max_nrandom())
+		return fail(S2TC_B200_EUNSUPPORTED, "S2TC_RANDOM_COLORS=%d exceeds the %d candidates the search kernel can hold in shared memory",
+				nrandom, pair_search_max_nrandom());
+	CU(c->ends.reserve((size_t) nblocks * sizeof(uint2)));
+	if (nrandom) {
+		CU(c->cand_c.reserve((size_t) nblocks * nrandom * sizeof(uint16_t)));
+		if (s.dxt == kDxt5)
+			CU(c->cand_a.reserve((size_t) nblocks * nrandom));
+		// jump polynomials for this slab: thread t starts at cursor0 + (blk0 + 32 t) * draws_per_block
+		const uint64_t dpb = (uint64_t) draws_per_block(s.dxt, nrandom);
+		if (c->plan_next == kPlanRing) { // ring exhausted: wait for the copies queued so far
+			CU(cudaStreamSynchronize(st));
+			c->plan_next = 0;
+		}
+		RandPlan *hp = &c->h_plans[c->plan_next];
+		RandPlan *dp = (RandPlan *) c->plans.p + c->plan_next;
+		c->plan_next++;
+		rand_plan_init(*hp, cursor0 + (uint64_t) blk0 * dpb, (uint64_t) kBlocksPerRandThread * dpb);
+		CU(cudaMemcpyAsync(dp, hp, sizeof(RandPlan), cudaMemcpyHostToDevice, st));
+		FamScope f(c, st, kFamCand, 1);
+		CU(launch_random_candidates(s.dxt, nrandom, v, dp, kBlocksPerRandThread, (uint16_t *) c->cand_c.p,
+				(uint8_t *) c->cand_a.p, st));
+	}
+	{
+		FamScope f(c, st, kFamSearch, 1);
+		CU(launch_pair_search(s.dxt, s.cd, nrandom, v, (const uint16_t *) c->cand_c.p, (const uint8_t *) c->cand_a.p,
+				(uint2 *) c->ends.p, st));
+	}
+	{
+		FamScope f(c, st, kFamFinish, 1);
+		CU(launch_finish(s.dxt, s.cd, s.refine, v, (const uint2 *) c->ends.p, d_dst, st));
+	}
+	return 0;
+}
+
+// d_src_rows: texel row 4*row0 of the image.  d_carry: device ints or NULL.
+int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int width, int height,
+		const void *d_src_rows, int row0, int row1, void *d_dst, uint64_t cursor0, int *d_carry, cudaStream_t st)
+{
+	const int bh = (height + 3) / 4, bw = (width + 3) / 4;
+	if (width <= 0 || height <= 0 || row0 < 0 || row1 > bh || row0 > row1)
+		return fail(S2TC_B200_EINVAL, "bad geometry %dx%d rows [%d,%d)", width, height, row0, row1);
+	if (row0 == row1)
+		return 0;
+	const int comps = srccomps == 3 ? 3 : 4;
+	const int abits = alpha_bits(s.dxt);
+	const int y0 = row0 * 4, y1 = row1 * 4 < height ? row1 * 4 : height;
+	const int rows = y1 - y0;
+	const size_t npix = (size_t) width * rows;
+
+	const uint8_t *texels = (const uint8_t *) d_src_rows;
+	int fmt = comps == 3 ? kSrcRGB8 : kSrcRGBA8;
+	size_t texel_bytes = comps;
+	if (s.dither == kDitherSimple) {
+		CU(c->reduced.reserve(npix * 4));
+		CU(c->dither_ws.reserve(dither_workspace_bytes(npix)));
+		int *carry = d_carry;
+		if (!carry) {
+			carry = (int *) c->small.p;
+			CU(cudaMemsetAsync(carry, 0, 4 * sizeof(int), st));
+		}
+		FamScope f(c, st, kFamPrepass, 3);
+		CU(launch_prepass_simple(d_src_rows, comps, abits, npix, c->reduced.p, carry, c->dither_ws.p, st));
+		texels = (const uint8_t *) c->reduced.p;
+		fmt = kSrcReduced;
+		texel_bytes = 4;
+	} else if (s.dither == kDitherFloyd) {
+		return fail(S2TC_B200_EUNSUPPORTED, "S2TC_DITHER_MODE=FLOYDSTEINBERG is not implemented on the device yet");
+	}
+
+	// MODE_NORMAL goes slab by slab to bound the candidate/endpoint workspaces
+	const bool fast = is_fast_mode(s.cd, s.nrandom);
+	long long rows_per_slab = fast ? (row1 - row0) : (kSlabBlocks / bw > 0 ? kSlabBlocks / bw : 1);
+	const int bs = block_bytes(s.dxt);
+	for (long long r = row0; r < row1; r += rows_per_slab) {
+		const int r1 = (int) (r + rows_per_slab < row1 ? r + rows_per_slab : row1);
+		const int sy0 = (int) r * 4 - y0, sy1 = (r1 * 4 < height ? r1 * 4 : height) - y0;
+		const ImageView v = make_view(texels + (size_t) sy0 * width * texel_bytes, width, sy1 - sy0, fmt, abits);
+		int rc = encode_view(c, s, v, (long long) r * bw, cursor0, (uint8_t *) d_dst + (size_t) (r - row0) * bw * bs, st);
+		if (rc)
+			return rc;
+	}
+	return 0;
+}
+
+bool is_pinned(const void *p)
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeHost;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *s2tc_b200_last_error(void) { return g_last_error.c_str(); }
+
+int s2tc_b200_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+int s2tc_b200_ctx_create(int device, s2tc_b200_ctx **out)
+{
+	if (!out)
+		return fail(S2TC_B200_EINVAL, "out is NULL");
+	*out = nullptr;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) {
+		cudaGetLastError();
+		return fail(S2TC_B200_ENODEVICE, "no CUDA device available (%s); this library has no CPU path",
+				e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+	}
+	if (device < 0 || device >= n)
+		return fail(S2TC_B200_EINVAL, "device %d out of range (have %d)", device, n);
+	CU(cudaSetDevice(device));
+	s2tc_b200_ctx *c = new s2tc_b200_ctx();
+	c->device = device;
+	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CU(cudaHostAlloc((void **) &c->h_plans, sizeof(RandPlan) * kPlanRing, cudaHostAllocDefault));
+	CU(cudaHostAlloc((void **) &c->h_carry, 4 * sizeof(int), cudaHostAllocDefault));
+	CU(cudaHostAlloc((void **) &c->h_summary, 12 * sizeof(uint64_t), cudaHostAllocDefault));
+	CU(cudaHostAlloc((void **) &c->h_block, 128, cudaHostAllocDefault));
+	CU(c->plans.reserve(sizeof(RandPlan) * kPlanRing));
+	CU(c->small.reserve(1024));
+	*out = c;
+	return 0;
+}
+
+void s2tc_b200_ctx_destroy(s2tc_b200_ctx *c)
+{
+	if (!c)
+		return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	for (auto &p : c->pending) {
+		cudaEventDestroy(p.a);
+		cudaEventDestroy(p.b);
+	}
+	DevBuf *bufs[] = {&c->src, &c->reduced, &c->out, &c->ends, &c->cand_c, &c->cand_a, &c->dither_ws, &c->plans, &c->small};
+	for (DevBuf *b : bufs)
+		b->release();
+	cudaFreeHost(c->h_plans);
+	cudaFreeHost(c->h_carry);
+	cudaFreeHost(c->h_summary);
+	cudaFreeHost(c->h_block);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+s2tc_b200_ctx *s2tc_b200_default_ctx(void)
+{
+	static std::mutex mu;
+	static s2tc_b200_ctx *ctx = nullptr;
+	std::lock_guard<std::mutex> lock(mu);
+	if (!ctx) {
+		const char *d = getenv("S2TC_B200_DEVICE");
+		if (s2tc_b200_ctx_create(d ? atoi(d) : 0, &ctx) != 0)
+			ctx = nullptr;
+	}
+	return ctx;
+}
+
+int s2tc_b200_encode_rows_device(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int srccomps, int width, int height,
+		const void *d_src_rows, int row0, int row1, void *d_dst, uint64_t rand_cursor0, int *carry, void *stream)
+{
+	if (!c || !d_src_rows || !d_dst)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	s2tc_b200_settings s;
+	if (int rc = settings_normalise(sin, s))
+		return rc;
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	int *d_carry = nullptr;
+	if (carry && s.dither == kDitherSimple) {
+		d_carry = (int *) c->small.p + 8;
+		memcpy(c->h_carry, carry, 4 * sizeof(int));
+		CU(cudaMemcpyAsync(d_carry, c->h_carry, 4 * sizeof(int), cudaMemcpyHostToDevice, st));
+	}
+	if (int rc = encode_rows(c, s, srccomps, width, height, d_src_rows, row0, row1, d_dst, rand_cursor0, d_carry, st))
+		return rc;
+	if (d_carry) {
+		CU(cudaMemcpyAsync(c->h_carry, d_carry, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		memcpy(carry, c->h_carry, 4 * sizeof(int));
+	}
+	return 0;
+}
+
+int s2tc_b200_dither_summary_device(s2tc_b200_ctx *c, int srccomps, int alphabits, int width, int height,
+		const void *d_src_rows, int row0, int row1, uint64_t maps[12], void *stream)
+{
+	if (!c || !d_src_rows || !maps)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	const int bh = (height + 3) / 4;
+	if (width <= 0 || height <= 0 || row0 < 0 || row1 > bh || row0 > row1)
+		return fail(S2TC_B200_EINVAL, "bad geometry");
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	const int comps = srccomps == 3 ? 3 : 4;
+	const int y0 = row0 * 4, y1 = row1 * 4 < height ? row1 * 4 : height;
+	const size_t npix = (size_t) width * (y1 - y0);
+	CarryMap *d_sum = (CarryMap *) ((uint8_t *) c->small.p + 256);
+	if (npix == 0) {
+		const int kinds[4] = {kChanShift3, kChanShift2, kChanShift3, alpha_chan_kind(comps, alphabits)};
+		for (int ch = 0; ch < 4; ++ch) {
+			CarryMap m;
+			map_identity(m, kinds[ch]);
+			memcpy(maps + 3 * ch, m.w, sizeof(m.w));
+		}
+		return 0;
+	}
+	CU(c->dither_ws.reserve(dither_workspace_bytes(npix)));
+	{
+		FamScope f(c, st, kFamPrepass, 2);
+		CU(launch_dither_summary(d_src_rows, comps, alphabits, npix, d_sum, c->dither_ws.p, st));
+	}
+	CU(cudaMemcpyAsync(c->h_summary, d_sum, 4 * sizeof(CarryMap), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	memcpy(maps, c->h_summary, 12 * sizeof(uint64_t));
+	return 0;
+}
+
+int s2tc_b200_carry_apply(const uint64_t map[3], int channel, int srccomps, int alphabits, int carry_in)
+{
+	CarryMap m;
+	memcpy(m.w, map, sizeof(m.w));
+	const int kind = channel == 1 ? kChanShift2 : (channel == 3 ? alpha_chan_kind(srccomps == 3 ? 3 : 4, alphabits) : kChanShift3);
+	return map_apply(m, kind, carry_in);
+}
+
+int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int srccomps, int width, int height,
+		const uint8_t *src, uint8_t *dest, int dst_row_stride, uint64_t *rand_cursor)
+{
+	if (!c || !src || !dest)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	s2tc_b200_settings s;
+	if (int rc = settings_normalise(sin, s))
+		return rc;
+	if (width <= 0 || height <= 0)
+		return 0; // the reference's loops simply do not run
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	const int comps = srccomps == 3 ? 3 : 4;
+	const int bw = (width + 3) / 4, bh = (height + 3) / 4, bs = block_bytes(s.dxt);
+	const size_t in_bytes = (size_t) width * height * comps;
+	const size_t tight = (size_t) bw * bs, out_bytes = tight * bh;
+	const uint64_t cursor = rand_cursor ? *rand_cursor : 0;
+
+	CU(c->src.reserve(in_bytes));
+	CU(c->out.reserve(out_bytes));
+	CU(cudaMemcpyAsync(c->src.p, src, in_bytes, cudaMemcpyHostToDevice, st));
+	if (int rc = encode_rows(c, s, comps, width, height, c->src.p, 0, bh, c->out.p, cursor, nullptr, st))
+		return rc;
+
+	// ref s2tc_libtxc_dxtn.cpp:243,261,279: a stride below width*2 (DXT1) / width*4 (DXT3/5) means tight rows
+	const size_t row_bytes = dst_row_stride >= width * (bs / 4) ? (size_t) dst_row_stride : tight;
+	if (row_bytes == tight) {
+		CU(cudaMemcpyAsync(dest, c->out.p, out_bytes, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+	} else if (row_bytes > tight) {
+		CU(cudaMemcpy2DAsync(dest, row_bytes, c->out.p, tight, tight, bh, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+	} else { // rows overlap in dest (stride between width*bs/4 and the padded width): later rows win, as in the reference
+		std::vector<uint8_t> tmp(out_bytes);
+		CU(cudaMemcpyAsync(tmp.data(), c->out.p, out_bytes, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		for (int r = 0; r < bh; ++r)
+			memcpy(dest + (size_t) r * row_bytes, tmp.data() + (size_t) r * tight, tight);
+	}
+	if (rand_cursor && s.nrandom > 0)
+		*rand_cursor = cursor + (uint64_t) bw * bh * draws_per_block(s.dxt, s.nrandom);
+	(void) is_pinned;
+	return 0;
+}
+
+int s2tc_b200_rgb565_host(s2tc_b200_ctx *c, uint8_t *out, const uint8_t *src, int width, int height, int srccomps,
+		int alphabits, int dither)
+{
+	if (!c || !out || !src)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	if (width <= 0 || height <= 0)
+		return 0;
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	const int comps = srccomps == 3 ? 3 : 4;
+	const int abits = (alphabits == 1 || alphabits == 4) ? alphabits : 8; // ref s2tc_algorithm.cpp:1437-1449
+	const size_t npix = (size_t) width * height;
+	CU(c->src.reserve(npix * comps));
+	CU(c->reduced.reserve(npix * 4));
+	CU(cudaMemcpyAsync(c->src.p, src, npix * comps, cudaMemcpyHostToDevice, st));
+	if (dither == kDitherNone) {
+		FamScope f(c, st, kFamPrepass, 1);
+		CU(launch_prepass_none(c->src.p, comps, abits, npix, c->reduced.p, st));
+	} else if (dither == kDitherFloyd) {
+		return fail(S2TC_B200_EUNSUPPORTED, "DITHER_FLOYDSTEINBERG is not implemented on the device yet");
+	} else {
+		CU(c->dither_ws.reserve(dither_workspace_bytes(npix)));
+		int *carry = (int *) c->small.p;
+		CU(cudaMemsetAsync(carry, 0, 4 * sizeof(int), st));
+		FamScope f(c, st, kFamPrepass, 3);
+		CU(launch_prepass_simple(c->src.p, comps, abits, npix, c->reduced.p, carry, c->dither_ws.p, st));
+	}
+	CU(cudaMemcpyAsync(out, c->reduced.p, npix * 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return 0;
+}
+
+int s2tc_b200_encode_block_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, uint8_t *out, const uint8_t *rgba, int iw,
+		int w, int h, uint64_t *rand_cursor)
+{
+	if (!c || !out || !rgba)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	if (w < 1 || w > 4 || h < 1 || h > 4)
+		return fail(S2TC_B200_EINVAL, "block extent %dx%d", w, h);
+	s2tc_b200_settings s;
+	if (int rc = settings_normalise(sin, s))
+		return rc;
+	s.dither = kDitherNone; // input is already reduced
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = c->stream;
+	for (int y = 0; y < h; ++y)
+		memcpy(c->h_block + (size_t) y * w * 4, rgba + (size_t) y * iw * 4, (size_t) w * 4);
+	uint8_t *d_px = (uint8_t *) c->small.p + 512, *d_out = d_px + 64;
+	CU(cudaMemcpyAsync(d_px, c->h_block, (size_t) w * h * 4, cudaMemcpyHostToDevice, st));
+	const ImageView v = make_view(d_px, w, h, kSrcReduced, alpha_bits(s.dxt));
+	const uint64_t cursor = rand_cursor ? *rand_cursor : 0;
+	if (int rc = encode_view(c, s, v, 0, cursor, d_out, st))
+		return rc;
+	const int bs = block_bytes(s.dxt);
+	CU(cudaMemcpyAsync(c->h_block + 64, d_out, bs, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	memcpy(out, c->h_block + 64, bs);
+	if (rand_cursor && s.nrandom > 0)
+		*rand_cursor = cursor + draws_per_block(s.dxt, s.nrandom);
+	return 0;
+}
+
+int s2tc_b200_transcode_device(s2tc_b200_ctx *c, int dxt, void *d_blocks, size_t nblocks, void *stream)
+{
+	if (!c || !d_blocks)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	if (dxt != kDxt1 && dxt != kDxt3 && dxt != kDxt5)
+		return fail(S2TC_B200_EINVAL, "bad dxt %d", dxt);
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	FamScope f(c, st, kFamTranscode, 1);
+	CU(launch_transcode(dxt, d_blocks, nblocks, st));
+	return 0;
+}
+
+int s2tc_b200_transcode_host(s2tc_b200_ctx *c, int dxt, uint8_t *blocks, size_t nblocks)
+{
+	if (!c || !blocks)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	if (dxt != kDxt1 && dxt != kDxt3 && dxt != kDxt5)
+		return fail(S2TC_B200_EINVAL, "bad dxt %d", dxt);
+	if (!nblocks)
+		return 0;
+	const size_t bytes = nblocks * block_bytes(dxt);
+	{
+		std::lock_guard<std::mutex> lock(c->mu);
+		CU(cudaSetDevice(c->device));
+		CU(c->out.reserve(bytes));
+		CU(cudaMemcpyAsync(c->out.p, blocks, bytes, cudaMemcpyHostToDevice, c->stream));
+	}
+	if (int rc = s2tc_b200_transcode_device(c, dxt, c->out.p, nblocks, nullptr))
+		return rc;
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaMemcpyAsync(blocks, c->out.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+static std::mutex g_cursor_mu;
+static uint64_t g_cursor = 0;
+uint64_t s2tc_b200_rand_cursor_get(void)
+{
+	std::lock_guard<std::mutex> lock(g_cursor_mu);
+	return g_cursor;
+}
+void s2tc_b200_rand_cursor_set(uint64_t draws)
+{
+	std::lock_guard<std::mutex> lock(g_cursor_mu);
+	g_cursor = draws;
+}
+
+int s2tc_b200_sync(s2tc_b200_ctx *c)
+{
+	if (!c)
+		return fail(S2TC_B200_EINVAL, "NULL context");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+uint64_t s2tc_b200_launch_count(s2tc_b200_ctx *c) { return c ? c->launches : 0; }
+
+int s2tc_b200_profile_enable(s2tc_b200_ctx *c, int on)
+{
+	if (!c)
+		return fail(S2TC_B200_EINVAL, "NULL context");
+	std::lock_guard<std::mutex> lock(c->mu);
+	c->profiling = on != 0;
+	return 0;
+}
+
+int s2tc_b200_profile_read(s2tc_b200_ctx *c, double ms[6], uint64_t launches[6], int reset)
+{
+	if (!c)
+		return fail(S2TC_B200_EINVAL, "NULL context");
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	CU(cudaDeviceSynchronize());
+	for (auto &p : c->pending) {
+		float t = 0;
+		if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess)
+			c->fam_ms[p.fam] += t;
+		cudaEventDestroy(p.a);
+		cudaEventDestroy(p.b);
+	}
+	c->pending.clear();
+	for (int i = 0; i < kNumFam; ++i) {
+		if (ms)
+			ms[i] = c->fam_ms[i];
+		if (launches)
+			launches[i] = c->fam_launches[i];
+		if (reset) {
+			c->fam_ms[i] = 0;
+			c->fam_launches[i] = 0;
+		}
+	}
+	return 0;
+}
+
+} // extern "C"

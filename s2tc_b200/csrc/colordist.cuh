@@ -1,0 +1,188 @@
+// colordist.cuh -- the eight S2TC colour metrics and the alpha metric, host+device.
+//
+// Each metric is split into a per-colour "feature" (everything that depends on one colour only:
+// squares for SRGB, the sqrt-luma triple for SRGB_MIXED, the unit vector for NORMALMAP) and a
+// pairwise distance on features.  The results are bit-identical to the reference's
+// color_dist_* functions (s2tc_algorithm.cpp:215-361); the split only removes recomputation
+// when one colour meets many others (distance matrix rows, 16 texels against two endpoints).
+//
+// Exactness notes:
+//  * SRGB overflows int32 for saturated pairs and the compiled reference wraps: products are
+//    done in uint32_t and shifted arithmetically.  SRGB is also NOT symmetric in its arguments
+//    (SHRR rounds -x and x differently), so callers keep the reference's argument order.
+//  * SRGB_MIXED needs a correctly rounded sqrtf and a separately rounded +0.5f.
+//  * NORMALMAP is a chain of individually rounded fp32 operations: no FMA contraction, IEEE
+//    division and square root.  On the device this is spelled with the _rn intrinsics so that no
+//    compiler flag can change it.
+#pragma once
+
+#include "s2tc_defs.h"
+
+#if !defined(__CUDA_ARCH__)
+#include <math.h>
+#endif
+
+namespace s2tc {
+
+// ---- individually rounded fp32 primitives --------------------------------------------------
+#if defined(__CUDA_ARCH__)
+S2TC_D float f_add(float a, float b) { return __fadd_rn(a, b); }
+S2TC_D float f_sub(float a, float b) { return __fsub_rn(a, b); }
+S2TC_D float f_mul(float a, float b) { return __fmul_rn(a, b); }
+S2TC_D float f_div(float a, float b) { return __fdiv_rn(a, b); }
+S2TC_D float f_sqrt(float a) { return __fsqrt_rn(a); }
+S2TC_D int f_trunc(float a) { return __float2int_rz(a); }
+#else
+// host build (tests only) is compiled with -ffp-contract=off; volatile blocks reassociation
+inline float f_add(float a, float b) { volatile float r = a + b; return r; }
+inline float f_sub(float a, float b) { volatile float r = a - b; return r; }
+inline float f_mul(float a, float b) { volatile float r = a * b; return r; }
+inline float f_div(float a, float b) { volatile float r = a / b; return r; }
+inline float f_sqrt(float a) { volatile float r = sqrtf(a); return r; }
+inline int f_trunc(float a) { return (int) a; }
+#endif
+
+// SHRR(a, n) = (a + (1 << (n-1))) >> n with wrapping add and arithmetic shift (ref :215)
+S2TC_HD int shrr(int a, int n) { return (int) ((uint32_t) a + (1u << (n - 1))) >> n; }
+S2TC_HD int wmul(int a, int b) { return (int) ((uint32_t) a * (uint32_t) b); }
+S2TC_HD int wadd(int a, int b) { return (int) ((uint32_t) a + (uint32_t) b); }
+
+S2TC_HD int alpha_dist(int a, int b) { return (a - b) * (a - b); } // ref :358-361
+
+// ---- texel packing ----------------------------------------------------------------------
+// A reduced texel is the 4 bytes {r5, g6, b5, a} read as a little-endian word.
+S2TC_HD int px_r(uint32_t p) { return (int) (p & 0xFF); }
+S2TC_HD int px_g(uint32_t p) { return (int) ((p >> 8) & 0xFF); }
+S2TC_HD int px_b(uint32_t p) { return (int) ((p >> 16) & 0xFF); }
+S2TC_HD int px_a(uint32_t p) { return (int) (p >> 24); }
+S2TC_HD uint32_t px_make(int r, int g, int b, int a = 0)
+{
+	return (uint32_t) r | ((uint32_t) g << 8) | ((uint32_t) b << 16) | ((uint32_t) a << 24);
+}
+S2TC_HD uint32_t px_rgb(uint32_t p) { return p & 0x00FFFFFFu; }
+
+// ---- metrics ----------------------------------------------------------------------------
+struct FeatRGB { int r, g, b; };
+struct FeatF3 { float x, y, z; };
+
+template <int CD> struct Metric;
+
+// linear metrics on the raw 5/6/5 differences
+template <int CD> struct LinearMetric {
+	typedef FeatRGB Feat;
+	static constexpr bool kMayBeNegative = false;
+	static S2TC_HD Feat feat(uint32_t p) { return Feat{px_r(p), px_g(p), px_b(p)}; }
+};
+
+template <> struct Metric<kAVG> : LinearMetric<kAVG> { // ref :217-223, <= 11657
+	static S2TC_HD int dist(const FeatRGB &a, const FeatRGB &b)
+	{
+		int dr = a.r - b.r, dg = a.g - b.g, db = a.b - b.b;
+		return ((dr * dr) << 2) + dg * dg + ((db * db) << 2);
+	}
+};
+template <> struct Metric<kW0AVG> : LinearMetric<kW0AVG> { // ref :225-232, <= 5891
+	static S2TC_HD int dist(const FeatRGB &a, const FeatRGB &b)
+	{
+		int dr = a.r - b.r, dg = a.g - b.g, db = a.b - b.b;
+		return dr * dr + dg * dg + db * db;
+	}
+};
+template <> struct Metric<kWAVG> : LinearMetric<kWAVG> { // ref :234-241, <= 20681
+	static S2TC_HD int dist(const FeatRGB &a, const FeatRGB &b)
+	{
+		int dr = a.r - b.r, dg = a.g - b.g, db = a.b - b.b;
+		return ((dr * dr) << 2) + ((dg * dg) << 2) + db * db;
+	}
+};
+template <> struct Metric<kYUV> : LinearMetric<kYUV> { // ref :243-254
+	static S2TC_HD int dist(const FeatRGB &a, const FeatRGB &b)
+	{
+		int dr = a.r - b.r, dg = a.g - b.g, db = a.b - b.b;
+		int y = dr * 60 + dg * 59 + db * 22;
+		int u = dr * 202 - y;
+		int v = db * 202 - y;
+		return ((y * y) << 1) + shrr(u * u, 3) + shrr(v * v, 4);
+	}
+};
+template <> struct Metric<kRGB> : LinearMetric<kRGB> { // ref :256-267
+	static S2TC_HD int dist(const FeatRGB &a, const FeatRGB &b)
+	{
+		int dr = a.r - b.r, dg = a.g - b.g, db = a.b - b.b;
+		int y = dr * 42 + dg * 72 + db * 14;
+		int u = dr * 202 - y;
+		int v = db * 202 - y;
+		return ((y * y) << 1) + shrr(u * u, 3) + shrr(v * v, 4);
+	}
+};
+
+template <> struct Metric<kSRGB> { // ref :269-283
+	typedef FeatRGB Feat; // squares of the components
+	static constexpr bool kMayBeNegative = true;
+	static S2TC_HD Feat feat(uint32_t p)
+	{
+		int r = px_r(p), g = px_g(p), b = px_b(p);
+		return Feat{r * r, g * g, b * b};
+	}
+	static S2TC_HD int dist(const FeatRGB &a, const FeatRGB &b)
+	{
+		int dr = a.r - b.r, dg = a.g - b.g, db = a.b - b.b;
+		int y = dr * 84 + dg * 72 + db * 28;
+		int u = dr * 409 - y;
+		int v = db * 409 - y;
+		int sy = wmul(shrr(y, 3), shrr(y, 4));
+		int su = wmul(shrr(u, 3), shrr(u, 4));
+		int sv = wmul(shrr(v, 3), shrr(v, 4));
+		return wadd(wadd(shrr(sy, 4), shrr(su, 8)), shrr(sv, 9));
+	}
+};
+
+template <> struct Metric<kSRGB_MIXED> { // ref :285-315
+	typedef FeatRGB Feat; // {Y, U, V} of one colour
+	static constexpr bool kMayBeNegative = false;
+	static S2TC_HD Feat feat(uint32_t p)
+	{
+		int r = px_r(p), g = px_g(p), b = px_b(p);
+		int lin = 37 * (r * r * 84 + g * g * 72 + b * b * 28); // < 2^24: exact in fp32
+		int y = f_trunc(f_add(f_sqrt((float) lin), 0.5f));
+		return Feat{y, r * 191 - y, b * 191 - y};
+	}
+	static S2TC_HD int dist(const FeatRGB &a, const FeatRGB &b)
+	{
+		int y = a.r - b.r, u = a.g - b.g, v = a.b - b.b;
+		return ((y * y) << 3) + shrr(u * u, 1) + shrr(v * v, 2);
+	}
+};
+
+template <> struct Metric<kNORMALMAP> { // ref :317-354
+	typedef FeatF3 Feat; // normalised direction
+	static constexpr bool kMayBeNegative = false;
+	static S2TC_HD Feat feat(uint32_t p)
+	{
+		float x = f_sub(f_mul(f_div((float) px_r(p), 31.0f), 2.0f), 1.0f);
+		float y = f_sub(f_mul(f_div((float) px_g(p), 63.0f), 2.0f), 1.0f);
+		float z = f_sub(f_mul(f_div((float) px_b(p), 31.0f), 2.0f), 1.0f);
+		float n = f_add(f_add(f_mul(x, x), f_mul(y, y)), f_mul(z, z));
+		if (n > 0) {
+			n = f_div(1.0f, f_sqrt(n));
+			x = f_mul(x, n);
+			y = f_mul(y, n);
+			z = f_mul(z, n);
+		}
+		return Feat{x, y, z};
+	}
+	static S2TC_HD int dist(const FeatF3 &a, const FeatF3 &b)
+	{
+		float dx = f_sub(b.x, a.x), dy = f_sub(b.y, a.y), dz = f_sub(b.z, a.z);
+		float s = f_add(f_add(f_mul(dx, dx), f_mul(dy, dy)), f_mul(dz, dz));
+		return f_trunc(f_mul(100000.0f, s));
+	}
+};
+
+// convenience: distance between two packed texels (used off the hot loops and by tests)
+template <int CD> S2TC_HD int color_dist(uint32_t a, uint32_t b)
+{
+	return Metric<CD>::dist(Metric<CD>::feat(a), Metric<CD>::feat(b));
+}
+
+} // namespace s2tc

@@ -1,0 +1,135 @@
+// kernels.cuh -- declarations shared by the CUDA translation units: the image view the encode
+// kernels read from, the block loader, and the host-callable launch wrappers.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "block_core.cuh"
+#include "dither_core.cuh"
+#include "glibc_rand.cuh"
+
+namespace s2tc {
+
+// A horizontal slab of an image in device memory.  `base` addresses texel row 0 of the slab; rows are
+// tightly packed (width * bytes_per_texel), as tx_compress_dxtn receives them
+// (ref s2tc_libtxc_dxtn.cpp:146, s2tc_algorithm.cpp:1274).
+struct ImageView {
+	const uint8_t *base;
+	int width;     // texels per row
+	int rows;      // texel rows in the slab
+	int fmt;       // SrcFormat
+	int alphabits; // 1 / 4 / 8, used when fmt is a raw format (fused DITHER_NONE)
+	int blocks_w;  // ceil(width / 4)
+	int blocks_h;  // ceil(rows / 4)
+};
+
+inline ImageView make_view(const void *base, int width, int rows, int fmt, int alphabits)
+{
+	ImageView v;
+	v.base = (const uint8_t *) base;
+	v.width = width;
+	v.rows = rows;
+	v.fmt = fmt;
+	v.alphabits = alphabits;
+	v.blocks_w = (width + 3) / 4;
+	v.blocks_h = (rows + 3) / 4;
+	return v;
+}
+
+#if defined(__CUDACC__)
+// fused DITHER_NONE on a raw RGBA word (ref s2tc_algorithm.cpp:1274-1297)
+__device__ __forceinline__ uint32_t reduce_word(uint32_t w, int alphabits)
+{
+	uint32_t rb = (w >> 3) & 0x001F001Fu;
+	uint32_t g = (w >> 2) & 0x00003F00u;
+	uint32_t a = alphabits == 8 ? (w & 0xFF000000u) : (alphabits == 4 ? ((w >> 4) & 0x0F000000u) : ((w >> 7) & 0x01000000u));
+	return rb | g | a;
+}
+
+// Loads block (bx, by) of the view into registers as reduced texels.  Full-width blocks of 4-byte
+// formats whose rows are 16-byte aligned take one 128-bit load per texel row; everything else
+// (edge blocks, odd widths, 3-byte texels) goes texel by texel.
+__device__ __forceinline__ void load_block(const ImageView &v, int bx, int by, Block &b)
+{
+	const int x0 = bx * 4, y0 = by * 4;
+	const int w = min(4, v.width - x0), h = min(4, v.rows - y0);
+	b.valid = valid_mask(w, h);
+	if (v.fmt != kSrcRGB8) {
+		const size_t pitch = (size_t) v.width * 4;
+		const uint8_t *p = v.base + (size_t) y0 * pitch + (size_t) x0 * 4;
+		const bool vec = w == 4 && ((pitch | (size_t) v.base) & 15) == 0;
+#pragma unroll
+		for (int y = 0; y < 4; ++y) {
+			uint32_t t[4] = {0, 0, 0, 0};
+			if (y < h) {
+				const uint8_t *row = p + (size_t) y * pitch;
+				if (vec) {
+					const uint4 q = __ldg(reinterpret_cast<const uint4 *>(row));
+					t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
+				} else {
+#pragma unroll
+					for (int x = 0; x < 4; ++x)
+						if (x < w)
+							t[x] = __ldg(reinterpret_cast<const uint32_t *>(row) + x);
+				}
+			}
+#pragma unroll
+			for (int x = 0; x < 4; ++x)
+				b.px[y * 4 + x] = v.fmt == kSrcRGBA8 ? reduce_word(t[x], v.alphabits) : t[x];
+		}
+	} else {
+		const size_t pitch = (size_t) v.width * 3;
+		const uint8_t *p = v.base + (size_t) y0 * pitch + (size_t) x0 * 3;
+		const uint32_t ones = ((1u << v.alphabits) - 1u) << 24;
+#pragma unroll
+		for (int y = 0; y < 4; ++y)
+#pragma unroll
+			for (int x = 0; x < 4; ++x) {
+				uint32_t t = 0;
+				if (y < h && x < w) {
+					const uint8_t *q = p + (size_t) y * pitch + x * 3;
+					t = (uint32_t) (__ldg(q) >> 3) | ((uint32_t) (__ldg(q + 1) >> 2) << 8) | ((uint32_t) (__ldg(q + 2) >> 3) << 16) | ones;
+				}
+				b.px[y * 4 + x] = t;
+			}
+	}
+}
+#endif
+
+// ---- launch wrappers (defined in the .cu files); all asynchronous on `stream` -------------------
+
+// MODE_FAST: candidates + refinement + packing in one pass, one thread per block.
+cudaError_t launch_fast_encode(int dxt, int cd, int refine, const ImageView &v, void *d_out, cudaStream_t stream);
+
+// MODE_NORMAL step 1 (nrandom > 0): random candidate colours for every block of the view.
+// d_cand_c: [blocks][nrandom] uint16 (565), d_cand_a: [blocks][nrandom] uint8 (DXT5 only)
+cudaError_t launch_random_candidates(int dxt, int nrandom, const ImageView &v, const RandPlan *d_plan,
+		int blocks_per_thread, uint16_t *d_cand_c, uint8_t *d_cand_a, cudaStream_t stream);
+
+// MODE_NORMAL step 2: the c0/c1 (and DXT5 a0/a1) pair search, a thread group per block.
+// d_ends: [blocks] uint2 {c0_565 | c1_565 << 16, a0 | a1 << 8}
+cudaError_t launch_pair_search(int dxt, int cd, int nrandom, const ImageView &v, const uint16_t *d_cand_c,
+		const uint8_t *d_cand_a, uint2 *d_ends, cudaStream_t stream);
+// largest nrandom the search kernel can hold in shared memory
+int pair_search_max_nrandom();
+
+// MODE_NORMAL step 3: refinement + packing from the searched endpoints, one thread per block.
+cudaError_t launch_finish(int dxt, int cd, int refine, const ImageView &v, const uint2 *d_ends, void *d_out,
+		cudaStream_t stream);
+
+// 565 pre-pass.
+cudaError_t launch_prepass_none(const void *d_src, int srccomps, int alphabits, size_t npixels, void *d_reduced,
+		cudaStream_t stream);
+// DITHER_SIMPLE over `npixels` texels in raster order.  d_carry: 4 ints (r,g,b,a) carried in and
+// updated to the carry out.  d_maps: workspace of dither_workspace_bytes(npixels).
+size_t dither_workspace_bytes(size_t npixels);
+cudaError_t launch_prepass_simple(const void *d_src, int srccomps, int alphabits, size_t npixels, void *d_reduced,
+		int *d_carry, void *d_workspace, cudaStream_t stream);
+// transfer maps only (for sharding a carry chain across GPUs): d_summary receives 4 CarryMaps
+cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits, size_t npixels,
+		CarryMap *d_summary, void *d_workspace, cudaStream_t stream);
+
+// S3TC -> S2TC transcode, in place.
+cudaError_t launch_transcode(int dxt, void *d_blocks, size_t nblocks, cudaStream_t stream);
+
+} // namespace s2tc

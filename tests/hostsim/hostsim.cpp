@@ -1,0 +1,251 @@
+// hostsim.cpp -- TEST-ONLY CPU build of the encoder's host+device headers (s2tc_b200/csrc/*.cuh).
+//
+// The per-block logic, the metric arithmetic, the rand() jump-ahead, the dither transfer maps and the
+// transcoder are written as __host__ __device__ code; this file instantiates them for the CPU and
+// walks an image the way the kernels do (same chunking, same per-thread rand segments), so that the
+// exact source the GPU runs can be checked against the oracle in the CPU-only test tier.
+// It is never linked into, loaded by, or reachable from the shipped library.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../s2tc_b200/csrc/block_core.cuh"
+#include "../../s2tc_b200/csrc/dither_core.cuh"
+#include "../../s2tc_b200/csrc/glibc_rand.cuh"
+#include "../../s2tc_b200/csrc/transcode_core.cuh"
+
+using namespace s2tc;
+
+namespace {
+
+constexpr int kChunk = 128, kTileChunks = 128;      // mirrors kernels_misc.cu
+constexpr int kBlocksPerRandThread = 32;              // mirrors api.cu
+
+void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, uint32_t *out)
+{
+	if (dither == kDitherNone) {
+		for (size_t i = 0; i < npix; ++i) {
+			const uint8_t *p = src + i * comps;
+			out[i] = reduce_none(p[0], p[1], p[2], comps == 4 ? p[3] : 0, abits, comps == 4);
+		}
+		return;
+	}
+	// DITHER_SIMPLE through the three phases of kernels_misc.cu
+	const int kinds[4] = {kChanShift3, kChanShift2, kChanShift3, alpha_chan_kind(comps, abits)};
+	std::vector<uint32_t> wide(npix);
+	for (size_t i = 0; i < npix; ++i) {
+		const uint8_t *p = src + i * comps;
+		wide[i] = (uint32_t) p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t) (comps == 4 ? p[3] : 0) << 24);
+	}
+	const size_t nchunks = (npix + kChunk - 1) / kChunk;
+	const size_t ntiles = (nchunks + kTileChunks - 1) / kTileChunks;
+	std::vector<CarryMap> prefix(ntiles * kTileChunks * 4), tilemap(ntiles * 4);
+	for (size_t t = 0; t < ntiles; ++t) {
+		CarryMap run[4];
+		for (int ch = 0; ch < 4; ++ch)
+			map_identity(run[ch], kinds[ch]);
+		for (int k = 0; k < kTileChunks; ++k) {
+			const size_t chunk = t * kTileChunks + k, first = chunk * kChunk;
+			const int count = first >= npix ? 0 : (int) std::min<size_t>(kChunk, npix - first);
+			for (int ch = 0; ch < 4; ++ch) {
+				prefix[chunk * 4 + ch] = run[ch];
+				CarryMap m;
+				map_of_run(m, kinds[ch], (const uint8_t *) (wide.data() + (count ? first : 0)) + ch, 4, count);
+				map_compose(run[ch], run[ch], m, kinds[ch]);
+			}
+		}
+		for (int ch = 0; ch < 4; ++ch)
+			tilemap[t * 4 + ch] = run[ch];
+	}
+	int carry[4] = {0, 0, 0, 0};
+	std::vector<int> tile_carry(ntiles * 4);
+	for (size_t t = 0; t < ntiles; ++t)
+		for (int ch = 0; ch < 4; ++ch) {
+			tile_carry[t * 4 + ch] = carry[ch];
+			carry[ch] = map_apply(tilemap[t * 4 + ch], kinds[ch], carry[ch]);
+		}
+	for (size_t chunk = 0; chunk < nchunks; ++chunk) {
+		const size_t first = chunk * kChunk;
+		const int count = (int) std::min<size_t>(kChunk, npix - first);
+		uint8_t *row = (uint8_t *) (wide.data() + first);
+		for (int ch = 0; ch < 4; ++ch) {
+			if (kinds[ch] == kChanCopy) {
+				if (comps != 4)
+					for (int i = 0; i < count; ++i)
+						row[i * 4 + 3] = (uint8_t) ((1u << abits) - 1u);
+				continue;
+			}
+			const int c0 = map_apply(prefix[chunk * 4 + ch], kinds[ch], tile_carry[(chunk / kTileChunks) * 4 + ch]);
+			replay_run(kinds[ch], c0, row + ch, 4, count, row + ch);
+		}
+	}
+	memcpy(out, wide.data(), npix * 4);
+}
+
+void load(const uint32_t *img, int width, int height, int bx, int by, Block &b)
+{
+	const int w = std::min(4, width - bx * 4), h = std::min(4, height - by * 4);
+	b.valid = valid_mask(w, h);
+	for (int y = 0; y < 4; ++y)
+		for (int x = 0; x < 4; ++x)
+			b.px[y * 4 + x] = (y < h && x < w) ? img[(size_t) (by * 4 + y) * width + bx * 4 + x] : 0;
+}
+
+template <int DXT, int CD>
+void encode_image(const uint32_t *img, int width, int height, int nrandom, int refine, uint64_t cursor, uint8_t *dest)
+{
+	const int bw = (width + 3) / 4, bh = (height + 3) / 4;
+	const bool fast = is_fast_mode(CD, nrandom);
+	const int nr = nrandom > 0 ? nrandom : 0;
+	RandPlan plan;
+	GlibcRand rng;
+	if (nr)
+		rand_plan_init(plan, cursor, (uint64_t) kBlocksPerRandThread * draws_per_block(DXT, nr));
+	std::vector<uint32_t> c(16 + nr + 2);
+	std::vector<uint8_t> ca(16 + nr + 2);
+	std::vector<int> d((size_t) (16 + nr + 3) * 16);
+	for (int blk = 0; blk < bw * bh; ++blk) {
+		Block b;
+		load(img, width, height, blk % bw, blk / bw, b);
+		uint32_t c0, c1;
+		int a0 = 0, a1 = 0;
+		if (fast) {
+			fast_candidates<DXT, CD>(b, c0, c1, a0, a1);
+		} else {
+			int n = gather_colors<DXT>(b, c.data(), ca.data());
+			int m = n;
+			if (nr) {
+				if (blk % kBlocksPerRandThread == 0) // a new "thread" seeks its own window
+					rand_plan_seek(plan, (uint32_t) (blk / kBlocksPerRandThread), rng);
+				const CandBox box = candidate_box(c.data(), ca.data(), n);
+				for (int k = 0; k < nr; ++k) {
+					const uint32_t p = draw_candidate<DXT>(box, rng);
+					c[n + k] = px_rgb(p);
+					ca[n + k] = (uint8_t) (p >> 24);
+				}
+				m = n + nr;
+			} else if (n == 1) {
+				c[1] = c[0];
+				ca[1] = ca[0];
+				m = n = 2;
+			}
+			search_colors_scalar<CD>(c.data(), n, m, d.data());
+			if (DXT == kDxt5)
+				search_alpha_scalar(ca.data(), n, m, d.data());
+			c0 = c[0];
+			c1 = c[1];
+			a0 = ca[0];
+			a1 = ca[1];
+		}
+		uint32_t w[4];
+		finish_block<DXT, CD>(b, refine, c0, c1, a0, a1, w);
+		memcpy(dest + (size_t) blk * block_bytes(DXT), w, block_bytes(DXT));
+	}
+}
+
+template <int DXT>
+void encode_cd(int cd, const uint32_t *img, int width, int height, int nrandom, int refine, uint64_t cursor, uint8_t *dest)
+{
+	switch (cd) {
+	case kRGB: encode_image<DXT, kRGB>(img, width, height, nrandom, refine, cursor, dest); break;
+	case kYUV: encode_image<DXT, kYUV>(img, width, height, nrandom, refine, cursor, dest); break;
+	case kSRGB: encode_image<DXT, kSRGB>(img, width, height, nrandom, refine, cursor, dest); break;
+	case kSRGB_MIXED: encode_image<DXT, kSRGB_MIXED>(img, width, height, nrandom, refine, cursor, dest); break;
+	case kAVG: encode_image<DXT, kAVG>(img, width, height, nrandom, refine, cursor, dest); break;
+	case kW0AVG: encode_image<DXT, kW0AVG>(img, width, height, nrandom, refine, cursor, dest); break;
+	case kNORMALMAP: encode_image<DXT, kNORMALMAP>(img, width, height, nrandom, refine, cursor, dest); break;
+	default: encode_image<DXT, kWAVG>(img, width, height, nrandom, refine, cursor, dest); break;
+	}
+}
+
+} // namespace
+
+extern "C" {
+
+// tight output; returns 0 or -1 (FLOYDSTEINBERG is not part of the shared code yet)
+int hostsim_compress(int srccomps, int width, int height, const uint8_t *src, int dxt, int cd, int nrandom, int refine,
+		int dither, uint64_t cursor, uint8_t *dest)
+{
+	if (dither == kDitherFloyd)
+		return -1;
+	const int comps = srccomps == 3 ? 3 : 4;
+	dxt = norm_dxt(dxt);
+	cd = norm_cd(cd);
+	refine = norm_refine(refine);
+	std::vector<uint32_t> img((size_t) width * height);
+	prepass(src, comps, alpha_bits(dxt), dither, img.size(), img.data());
+	switch (dxt) {
+	case kDxt1: encode_cd<kDxt1>(cd, img.data(), width, height, nrandom, refine, cursor, dest); break;
+	case kDxt3: encode_cd<kDxt3>(cd, img.data(), width, height, nrandom, refine, cursor, dest); break;
+	default: encode_cd<kDxt5>(cd, img.data(), width, height, nrandom, refine, cursor, dest); break;
+	}
+	return 0;
+}
+
+int hostsim_prepass(int srccomps, int abits, int dither, size_t npix, const uint8_t *src, uint8_t *out)
+{
+	if (dither == kDitherFloyd)
+		return -1;
+	prepass(src, srccomps == 3 ? 3 : 4, abits, dither, npix, (uint32_t *) out);
+	return 0;
+}
+
+void hostsim_transcode(int dxt, uint8_t *blocks, size_t nblocks)
+{
+	for (size_t i = 0; i < nblocks; ++i) {
+		if (dxt == kDxt1) {
+			uint32_t w[2];
+			memcpy(w, blocks + i * 8, 8);
+			transcode_color_dxt1(w[0], w[1]);
+			memcpy(blocks + i * 8, w, 8);
+		} else {
+			uint32_t w[4];
+			memcpy(w, blocks + i * 16, 16);
+			transcode_color_opaque(w[2], w[3]);
+			if (dxt == kDxt5) {
+				uint64_t a = transcode_alpha_dxt5((uint64_t) w[0] | ((uint64_t) w[1] << 32));
+				w[0] = (uint32_t) a;
+				w[1] = (uint32_t) (a >> 32);
+			}
+			memcpy(blocks + i * 16, w, 16);
+		}
+	}
+}
+
+// exhaustive check of the reciprocal-multiply division used for the cluster means
+int hostsim_check_division(void)
+{
+	for (int n = 1; n <= 16; ++n)
+		for (int x = 0; x < 8192; ++x)
+			if (div_by_2n(x, half_recip18(n)) != x / (2 * n))
+				return 1000 * n + 1;
+	return 0;
+}
+
+int hostsim_rand(uint64_t cursor, uint64_t stride, uint32_t t, int n, int *out)
+{
+	RandPlan plan;
+	GlibcRand g;
+	rand_plan_init(plan, cursor, stride);
+	rand_plan_seek(plan, t, g);
+	for (int i = 0; i < n; ++i)
+		out[i] = g.next();
+	return 0;
+}
+
+int hostsim_color_dist(int cd, uint32_t a, uint32_t b)
+{
+	switch (cd) {
+	case kRGB: return color_dist<kRGB>(a, b);
+	case kYUV: return color_dist<kYUV>(a, b);
+	case kSRGB: return color_dist<kSRGB>(a, b);
+	case kSRGB_MIXED: return color_dist<kSRGB_MIXED>(a, b);
+	case kAVG: return color_dist<kAVG>(a, b);
+	case kW0AVG: return color_dist<kW0AVG>(a, b);
+	case kNORMALMAP: return color_dist<kNORMALMAP>(a, b);
+	default: return color_dist<kWAVG>(a, b);
+	}
+}
+
+} // extern "C"
