@@ -118,6 +118,9 @@ uint64_t s2tc_b200_launch_count(s2tc_b200_ctx *ctx);
 int s2tc_b200_profile_enable(s2tc_b200_ctx *ctx, int on);
 int s2tc_b200_profile_read(s2tc_b200_ctx *ctx, double ms[6], uint64_t launches[6], int reset);
 
+/* sustained INT32 (min + add) rate of the device in Gop/s: roofline denominator of the search kernels */
+int s2tc_b200_int32_peak(s2tc_b200_ctx *ctx, double *gops);
+
 #ifdef __cplusplus
 }
 #endif

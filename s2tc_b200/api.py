@@ -144,6 +144,7 @@ def lib():
     L.s2tc_b200_launch_count.restype = u64
     L.s2tc_b200_profile_enable.argtypes = [vp, i32]
     L.s2tc_b200_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), i32]
+    L.s2tc_b200_int32_peak.argtypes = [vp, C.POINTER(C.c_double)]
     L.tx_compress_dxtn.argtypes = [i32, i32, i32, vp, C.c_uint, vp, i32]
     L.tx_compress_dxtn.restype = None
     L.rgb565_image.argtypes = [vp, vp, i32, i32, i32, i32, i32]
@@ -277,6 +278,11 @@ class Encoder:
 
     def launch_count(self):
         return int(lib().s2tc_b200_launch_count(self._ctx))
+
+    def int32_peak_gops(self):
+        g = C.c_double()
+        _check(lib().s2tc_b200_int32_peak(self._ctx, C.byref(g)))
+        return g.value
 
     def profile(self, on=True):
         _check(lib().s2tc_b200_profile_enable(self._ctx, 1 if on else 0))

@@ -560,6 +560,35 @@ int s2tc_b200_sync(s2tc_b200_ctx *c)
 
 uint64_t s2tc_b200_launch_count(s2tc_b200_ctx *c) { return c ? c->launches : 0; }
 
+int s2tc_b200_int32_peak(s2tc_b200_ctx *c, double *gops)
+{
+	if (!c || !gops)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	const int iters = 1 << 14, ctas = 148 * 16;
+	int *sink = (int *) c->small.p + 200;
+	cudaEvent_t a, b;
+	CU(cudaEventCreate(&a));
+	CU(cudaEventCreate(&b));
+	double best = 0;
+	for (int rep = 0; rep < 4; ++rep) { // first repetition warms up
+		CU(cudaEventRecord(a, c->stream));
+		CU(launch_int32_peak(iters, ctas, sink, c->stream));
+		CU(cudaEventRecord(b, c->stream));
+		CU(cudaEventSynchronize(b));
+		float ms = 0;
+		CU(cudaEventElapsedTime(&ms, a, b));
+		const double ops = 2.0 * 8.0 * iters * 256.0 * ctas;
+		if (rep && ms > 0 && ops / ms * 1e-6 > best)
+			best = ops / ms * 1e-6;
+	}
+	cudaEventDestroy(a);
+	cudaEventDestroy(b);
+	*gops = best;
+	return 0;
+}
+
 int s2tc_b200_profile_enable(s2tc_b200_ctx *c, int on)
 {
 	if (!c)

@@ -132,4 +132,7 @@ cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits
 // S3TC -> S2TC transcode, in place.
 cudaError_t launch_transcode(int dxt, void *d_blocks, size_t nblocks, cudaStream_t stream);
 
+// measurement aid: `ctas` CTAs of 256 threads each run iters * 8 (min, add) pairs per thread
+cudaError_t launch_int32_peak(int iters, int ctas, int *d_sink, cudaStream_t stream);
+
 } // namespace s2tc

@@ -364,4 +364,38 @@ cudaError_t launch_transcode(int dxt, void *d_blocks, size_t nblocks, cudaStream
 	return cudaGetLastError();
 }
 
+// =====================================================================================================
+// Measurement aid: sustained INT32 min+add issue rate, the denominator for the search kernels' roofline
+// (search modes are bound by the integer pipes, not by HBM).  8 independent chains per
+// thread of exactly the two operations the pair scan is made of (IMNMX + IADD).
+// =====================================================================================================
+__global__ void __launch_bounds__(256) int32_peak_kernel(int iters, int seed, int *sink)
+{
+	int a[8], s[8];
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		a[k] = seed + threadIdx.x * (k + 1);
+		s[k] = 0;
+	}
+	int b = seed ^ (blockIdx.x << 8);
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int k = 0; k < 8; ++k)
+			s[k] += min(a[k], b); // the pair scan's inner operation: accumulate the smaller distance
+		b += 3;
+	}
+	int r = 0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k)
+		r ^= s[k];
+	if (r == 0x7FFFFFFF)
+		*sink = r;
+}
+
+cudaError_t launch_int32_peak(int iters, int ctas, int *d_sink, cudaStream_t stream)
+{
+	int32_peak_kernel<<<ctas, 256, 0, stream>>>(iters, 12345, d_sink);
+	return cudaGetLastError();
+}
+
 } // namespace s2tc

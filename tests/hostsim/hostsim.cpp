@@ -22,7 +22,8 @@ namespace {
 constexpr int kChunk = 128, kTileChunks = 128;      // mirrors kernels_misc.cu
 constexpr int kBlocksPerRandThread = 32;              // mirrors api.cu
 
-void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, uint32_t *out)
+void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, uint32_t *out,
+		int *carry_io = nullptr, CarryMap *summary = nullptr)
 {
 	if (dither == kDitherNone) {
 		for (size_t i = 0; i < npix; ++i) {
@@ -58,13 +59,25 @@ void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, 
 		for (int ch = 0; ch < 4; ++ch)
 			tilemap[t * 4 + ch] = run[ch];
 	}
+	if (summary) { // transfer function of the whole range = composition of the tile maps
+		for (int ch = 0; ch < 4; ++ch) {
+			map_identity(summary[ch], kinds[ch]);
+			for (size_t t = 0; t < ntiles; ++t)
+				map_compose(summary[ch], summary[ch], tilemap[t * 4 + ch], kinds[ch]);
+		}
+		return;
+	}
 	int carry[4] = {0, 0, 0, 0};
+	if (carry_io)
+		memcpy(carry, carry_io, sizeof(carry));
 	std::vector<int> tile_carry(ntiles * 4);
 	for (size_t t = 0; t < ntiles; ++t)
 		for (int ch = 0; ch < 4; ++ch) {
 			tile_carry[t * 4 + ch] = carry[ch];
 			carry[ch] = map_apply(tilemap[t * 4 + ch], kinds[ch], carry[ch]);
 		}
+	if (carry_io)
+		memcpy(carry_io, carry, sizeof(carry));
 	for (size_t chunk = 0; chunk < nchunks; ++chunk) {
 		const size_t first = chunk * kChunk;
 		const int count = (int) std::min<size_t>(kChunk, npix - first);
@@ -189,6 +202,21 @@ int hostsim_prepass(int srccomps, int abits, int dither, size_t npix, const uint
 		return -1;
 	prepass(src, srccomps == 3 ? 3 : 4, abits, dither, npix, (uint32_t *) out);
 	return 0;
+}
+
+// DITHER_SIMPLE over a texel range with an explicit carry in/out (what one shard of a sharded image runs)
+void hostsim_prepass_range(int srccomps, int abits, size_t npix, const uint8_t *src, int *carry_io, uint8_t *out)
+{
+	prepass(src, srccomps == 3 ? 3 : 4, abits, kDitherSimple, npix, (uint32_t *) out, carry_io);
+}
+
+// the range's transfer function: 4 channels x 3 words, the layout s2tc_b200_dither_summary_device returns
+void hostsim_dither_summary(int srccomps, int abits, size_t npix, const uint8_t *src, uint64_t *maps)
+{
+	CarryMap m[4];
+	prepass(src, srccomps == 3 ? 3 : 4, abits, kDitherSimple, npix, nullptr, nullptr, m);
+	for (int ch = 0; ch < 4; ++ch)
+		memcpy(maps + 3 * ch, m[ch].w, sizeof(m[ch].w));
 }
 
 void hostsim_transcode(int dxt, uint8_t *blocks, size_t nblocks)
