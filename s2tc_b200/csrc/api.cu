@@ -146,6 +146,11 @@ int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &
 		return 0;
 	}
 	const int nrandom = s.nrandom > 0 ? s.nrandom : 0;
+	if (nrandom == 0 && !getenv("S2TC_B200_FORCE_GROUP_SEARCH")) { // <= 16 candidates: the fused register-resident encoder
+		FamScope f(c, st, kFamSearch, 1);
+		CU(launch_encode16(s.dxt, s.cd, s.refine, v, d_dst, st));
+		return 0;
+	}
 	if (nrandom > pair_search_max_nrandom())
 		return fail(S2TC_B200_EUNSUPPORTED, "S2TC_RANDOM_COLORS=%d exceeds the %d candidates the search kernel can hold in shared memory",
 				nrandom, pair_search_max_nrandom());
