@@ -8,7 +8,7 @@
 One "step" = one pass of the hot path (565 pre-pass -> [random candidates] -> pair search -> refinement
 and packing, or the fused fast kernel) over one texture resident in HBM.  At N > 1 every rank owns a
 contiguous range of block rows of one tall texture (weak scaling: 8192-row shard per GPU); the only
-exchange is the DITHER_SIMPLE carry (a 96-byte transfer function per rank).
+exchange is the DITHER_SIMPLE carry (a 128-byte transfer function per rank).
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` goes through the
 reference-facing host call with host<->device copies in the timed region, `roofline` is for the
@@ -214,10 +214,9 @@ def main():
     # bracket exactly those launches (the legacy default stream's handle is 0 = "use the context's own")
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    maps_dev = torch.zeros(12, dtype=torch.int64, device="cuda") if world > 1 else None
-
+    
     def incoming_carry():
-        """DITHER_SIMPLE across shards: all-gather the 96-byte transfer functions, fold the lower ranks."""
+        """DITHER_SIMPLE across shards: all-gather the 128-byte transfer functions, fold the lower ranks."""
         if world == 1 or st.dither != 1:
             return None
         maps = enc.dither_summary_device(d_src, width, total_h, 4, abits, row0, row1, stream=stream.cuda_stream)

@@ -84,12 +84,13 @@ int s2tc_b200_compress_host(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int
 int s2tc_b200_encode_rows_device(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int srccomps, int width, int height,
 		const void *d_src_rows, int row0, int row1, void *d_dst, uint64_t rand_cursor0, int *carry, void *stream);
 
-/* DITHER_SIMPLE transfer function of the texel rows of block rows [row0,row1): 4 channels x 3 words.
+/* DITHER_SIMPLE transfer function of the texel rows of block rows [row0,row1): 4 channels x 32 bytes
+ * (byte k of a channel = carry state out for carry state k in; 1-bit alpha: byte 0 = sum mod 255).
  * s2tc_b200_carry_apply(map, channel, srccomps, alphabits, carry_in) evaluates one on the host, so a
- * set of shards can resolve their incoming carries with one tiny exchange. */
+ * set of shards can resolve their incoming carries with one 128-byte exchange. */
 int s2tc_b200_dither_summary_device(s2tc_b200_ctx *ctx, int srccomps, int alphabits, int width, int height,
-		const void *d_src_rows, int row0, int row1, uint64_t maps[12], void *stream);
-int s2tc_b200_carry_apply(const uint64_t map[3], int channel, int srccomps, int alphabits, int carry_in);
+		const void *d_src_rows, int row0, int row1, uint64_t maps[16], void *stream);
+int s2tc_b200_carry_apply(const uint64_t map[4], int channel, int srccomps, int alphabits, int carry_in);
 
 /* ---- 565 pre-pass only: backs the exported rgb565_image (ref s2tc_algorithm.h:38) ------------- */
 int s2tc_b200_rgb565_host(s2tc_b200_ctx *ctx, uint8_t *out, const uint8_t *src, int width, int height, int srccomps,

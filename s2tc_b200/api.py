@@ -255,17 +255,17 @@ class Encoder:
             carry[:] = list(arr)
 
     def dither_summary_device(self, src_rows, width, height, comps, alphabits, row0, row1, stream=None):
-        maps = (C.c_uint64 * 12)()
+        maps = (C.c_uint64 * 16)()
         _check(lib().s2tc_b200_dither_summary_device(self._ctx, comps, alphabits, width, height, _addr(src_rows), row0, row1,
                                                      maps, stream))
         return list(maps)
 
     @staticmethod
     def carry_apply(maps, comps, alphabits, carry):
-        """Carry leaving a texel range with transfer maps `maps` (12 words) for an incoming carry (4 ints)."""
+        """Carry leaving a texel range with transfer maps `maps` (16 words) for an incoming carry (4 ints)."""
         out = []
         for ch in range(4):
-            m = (C.c_uint64 * 3)(*maps[3 * ch:3 * ch + 3])
+            m = (C.c_uint64 * 4)(*maps[4 * ch:4 * ch + 4])
             out.append(lib().s2tc_b200_carry_apply(m, ch, comps, alphabits, carry[ch]))
         return out
 

@@ -85,7 +85,7 @@ struct s2tc_b200_ctx {
 	RandPlan *h_plans = nullptr; // pinned ring
 	int plan_next = 0;
 	int *h_carry = nullptr; // pinned, 4 ints
-	uint64_t *h_summary = nullptr; // pinned, 12 words
+	uint64_t *h_summary = nullptr; // pinned, 16 words
 	uint8_t *h_block = nullptr;   // pinned, 64 + 16 bytes for the single-block path
 	uint64_t launches = 0;
 	bool profiling = false;
@@ -282,7 +282,7 @@ int s2tc_b200_ctx_create(int device, s2tc_b200_ctx **out)
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CU(cudaHostAlloc((void **) &c->h_plans, sizeof(RandPlan) * kPlanRing, cudaHostAllocDefault));
 	CU(cudaHostAlloc((void **) &c->h_carry, 4 * sizeof(int), cudaHostAllocDefault));
-	CU(cudaHostAlloc((void **) &c->h_summary, 12 * sizeof(uint64_t), cudaHostAllocDefault));
+	CU(cudaHostAlloc((void **) &c->h_summary, 16 * sizeof(uint64_t), cudaHostAllocDefault));
 	CU(cudaHostAlloc((void **) &c->h_block, 128, cudaHostAllocDefault));
 	CU(c->plans.reserve(sizeof(RandPlan) * kPlanRing));
 	CU(c->small.reserve(1024));
@@ -352,7 +352,7 @@ int s2tc_b200_encode_rows_device(s2tc_b200_ctx *c, const s2tc_b200_settings *sin
 }
 
 int s2tc_b200_dither_summary_device(s2tc_b200_ctx *c, int srccomps, int alphabits, int width, int height,
-		const void *d_src_rows, int row0, int row1, uint64_t maps[12], void *stream)
+		const void *d_src_rows, int row0, int row1, uint64_t maps[16], void *stream)
 {
 	if (!c || !d_src_rows || !maps)
 		return fail(S2TC_B200_EINVAL, "NULL argument");
@@ -365,13 +365,13 @@ int s2tc_b200_dither_summary_device(s2tc_b200_ctx *c, int srccomps, int alphabit
 	const int comps = srccomps == 3 ? 3 : 4;
 	const int y0 = row0 * 4, y1 = row1 * 4 < height ? row1 * 4 : height;
 	const size_t npix = (size_t) width * (y1 - y0);
-	CarryMap *d_sum = (CarryMap *) ((uint8_t *) c->small.p + 256);
+	ByteMap *d_sum = (ByteMap *) ((uint8_t *) c->small.p + 256);
 	if (npix == 0) {
 		const int kinds[4] = {kChanShift3, kChanShift2, kChanShift3, alpha_chan_kind(comps, alphabits)};
 		for (int ch = 0; ch < 4; ++ch) {
-			CarryMap m;
-			map_identity(m, kinds[ch]);
-			memcpy(maps + 3 * ch, m.w, sizeof(m.w));
+			ByteMap m;
+			bmap_identity(m, kinds[ch]);
+			memcpy(maps + 4 * ch, m.e, sizeof(m.e));
 		}
 		return 0;
 	}
@@ -380,18 +380,18 @@ int s2tc_b200_dither_summary_device(s2tc_b200_ctx *c, int srccomps, int alphabit
 		FamScope f(c, st, kFamPrepass, 2);
 		CU(launch_dither_summary(d_src_rows, comps, alphabits, npix, d_sum, c->dither_ws.p, st));
 	}
-	CU(cudaMemcpyAsync(c->h_summary, d_sum, 4 * sizeof(CarryMap), cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(c->h_summary, d_sum, 4 * sizeof(ByteMap), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
-	memcpy(maps, c->h_summary, 12 * sizeof(uint64_t));
+	memcpy(maps, c->h_summary, 16 * sizeof(uint64_t));
 	return 0;
 }
 
-int s2tc_b200_carry_apply(const uint64_t map[3], int channel, int srccomps, int alphabits, int carry_in)
+int s2tc_b200_carry_apply(const uint64_t map[4], int channel, int srccomps, int alphabits, int carry_in)
 {
-	CarryMap m;
-	memcpy(m.w, map, sizeof(m.w));
+	ByteMap m;
+	memcpy(m.e, map, sizeof(m.e));
 	const int kind = channel == 1 ? kChanShift2 : (channel == 3 ? alpha_chan_kind(srccomps == 3 ? 3 : 4, alphabits) : kChanShift3);
-	return map_apply(m, kind, carry_in);
+	return bmap_apply(m, kind, carry_in);
 }
 
 int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int srccomps, int width, int height,

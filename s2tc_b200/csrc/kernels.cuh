@@ -137,9 +137,9 @@ cudaError_t launch_prepass_none(const void *d_src, int srccomps, int alphabits, 
 size_t dither_workspace_bytes(size_t npixels);
 cudaError_t launch_prepass_simple(const void *d_src, int srccomps, int alphabits, size_t npixels, void *d_reduced,
 		int *d_carry, void *d_workspace, cudaStream_t stream);
-// transfer maps only (for sharding a carry chain across GPUs): d_summary receives 4 CarryMaps
+// transfer maps only (for sharding a carry chain across GPUs): d_summary receives 4 ByteMaps
 cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits, size_t npixels,
-		CarryMap *d_summary, void *d_workspace, cudaStream_t stream);
+		ByteMap *d_summary, void *d_workspace, cudaStream_t stream);
 
 // S3TC -> S2TC transcode, in place.
 cudaError_t launch_transcode(int dxt, void *d_blocks, size_t nblocks, cudaStream_t stream);

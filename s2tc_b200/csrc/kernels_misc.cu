@@ -41,103 +41,106 @@ cudaError_t launch_prepass_none(const void *d_src, int srccomps, int alphabits, 
 // =====================================================================================================
 // DITHER_SIMPLE (reference s2tc_algorithm.cpp:1307-1349): one carry per channel runs through the whole
 // image in raster order.  Texels are cut into chunks of kChunk (one thread each), 128 chunks per CTA tile.
-//   phase 1  dither_maps_kernel : per chunk, the transfer map carry-in -> carry-out of every channel
-//                                 (all start states advanced together); a Hillis-Steele scan inside the
-//                                 CTA turns them into "tile start -> chunk start" prefix maps + a tile map
-//   phase 2  dither_scan_kernel : one CTA walks the tile maps from the true carry-in and leaves every
-//                                 tile's starting carry (or, for sharding, the composed map of the range)
-//   phase 3  dither_apply_kernel: every chunk replays the recurrence from its now-known carry
+//   phase 1  dither_maps_kernel : per chunk, the transfer map carry-in -> carry-out of every channel,
+//                                 built right to left with byte permutes (dither_core.cuh); a tree
+//                                 reduction inside the CTA composes them into the tile's map
+//   phase 2  dither_scan_kernel : one CTA composes / walks the tile maps from the true carry-in and leaves
+//                                 every tile's starting carry (or, for sharding, the map of the whole range)
+//   phase 3  dither_apply_kernel: walks the tile's chunk maps to every chunk's carry, then every thread
+//                                 streams its own 512-byte chunk (128-bit loads/stores, 8 in flight) and
+//                                 replays the recurrence
 // =====================================================================================================
 constexpr int kChunk = 128;       // texels per thread
 constexpr int kTileThreads = 128; // chunks per CTA
 constexpr int kTilePixels = kChunk * kTileThreads;
-constexpr int kTilePitch = kChunk + 1; // words; +1 keeps the per-thread row walks bank-conflict free
-
-struct ChanKinds { int k[4]; };
-
-static ChanKinds chan_kinds(int srccomps, int alphabits)
-{
-	ChanKinds c;
-	c.k[0] = kChanShift3;
-	c.k[1] = kChanShift2;
-	c.k[2] = kChanShift3;
-	c.k[3] = alpha_chan_kind(srccomps, alphabits);
-	return c;
-}
-
-// stage one tile of source texels in shared memory as 4-byte words (3-byte sources are widened)
-__device__ __forceinline__ void load_tile(const uint8_t *__restrict__ src, int srccomps, size_t npixels, size_t tile0,
-		uint32_t *tile)
-{
-	for (int k = threadIdx.x; k < kTilePixels; k += kTileThreads) {
-		const size_t p = tile0 + k;
-		uint32_t w = 0;
-		if (p < npixels) {
-			if (srccomps == 4)
-				w = __ldg(reinterpret_cast<const uint32_t *>(src) + p);
-			else {
-				const uint8_t *q = src + p * 3;
-				w = (uint32_t) __ldg(q) | ((uint32_t) __ldg(q + 1) << 8) | ((uint32_t) __ldg(q + 2) << 16);
-			}
-		}
-		tile[(k / kChunk) * kTilePitch + (k % kChunk)] = w;
-	}
-}
 
 __global__ void __launch_bounds__(kTileThreads)
 dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kinds, size_t npixels,
-		CarryMap *__restrict__ prefix /* [chunks][4] */, CarryMap *__restrict__ tilemaps /* [tiles][4] */)
+		const DitherLut *__restrict__ lut, ByteMap *__restrict__ chunkmaps /* [chunks][4] */,
+		ByteMap *__restrict__ tilemaps /* [tiles][4] */)
 {
-	extern __shared__ __align__(16) uint32_t tile[];
-	const size_t tile0 = (size_t) blockIdx.x * kTilePixels;
-	load_tile(src, srccomps, npixels, tile0, tile);
-	__syncthreads();
-
+	__shared__ __align__(16) uint32_t s_lut3[256][4];
+	__shared__ uint32_t s_lut2[256];
+	__shared__ ByteMap s_maps[kTileThreads][4];
 	const int t = threadIdx.x;
-	const size_t first = tile0 + (size_t) t * kChunk;
-	const int count = first >= npixels ? 0 : (int) min((size_t) kChunk, npixels - first);
-	CarryMap mine[4];
-	const uint8_t *row = reinterpret_cast<const uint8_t *>(tile + t * kTilePitch);
-#pragma unroll
-	for (int ch = 0; ch < 4; ++ch)
-		map_of_run(mine[ch], kinds.k[ch], row + ch, 4, count);
+	for (int i = t; i < 256 * 4; i += kTileThreads)
+		(&s_lut3[0][0])[i] = (&lut->lut3[0][0])[i];
+	for (int i = t; i < 256; i += kTileThreads)
+		s_lut2[i] = lut->lut2[i];
 	__syncthreads();
 
-	// inclusive scan of the maps across the tile, reusing the texel staging area: buf[2][128][4]
-	CarryMap *buf = reinterpret_cast<CarryMap *>(tile);
-	int cur = 0;
-#pragma unroll
-	for (int ch = 0; ch < 4; ++ch)
-		buf[t * 4 + ch] = mine[ch];
-	__syncthreads();
-	for (int d = 1; d < kTileThreads; d <<= 1) {
-		CarryMap *in = buf + cur * kTileThreads * 4, *out = buf + (cur ^ 1) * kTileThreads * 4;
-#pragma unroll
-		for (int ch = 0; ch < 4; ++ch) {
-			if (t >= d) {
-				CarryMap r;
-				map_compose(r, in[(t - d) * 4 + ch], in[t * 4 + ch], kinds.k[ch]);
-				out[t * 4 + ch] = r;
-			} else {
-				out[t * 4 + ch] = in[t * 4 + ch];
-			}
+	const size_t first = ((size_t) blockIdx.x * kTileThreads + t) * kChunk;
+	const int count = first >= npixels ? 0 : (int) min((size_t) kChunk, npixels - first);
+	RgbTables tab;
+	rgb_tables_init(tab);
+	uint32_t asum = 0;
+	if (srccomps == 4 && count == kChunk && ((size_t) src & 15) == 0) {
+		// two half-chunks advance together (two independent dependency chains per channel), joined at the end
+		const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(src) + first);
+		RgbTables left;
+		rgb_tables_init(left);
+#pragma unroll 2
+		for (int i = kChunk / 8 - 1; i >= 0; --i) { // right to left, four texels per 128-bit load
+			const uint4 ql = __ldg(p + i), qr = __ldg(p + kChunk / 8 + i);
+			rgb_tables_prepend(left, ql.w, s_lut3, s_lut2);
+			rgb_tables_prepend(tab, qr.w, s_lut3, s_lut2);
+			rgb_tables_prepend(left, ql.z, s_lut3, s_lut2);
+			rgb_tables_prepend(tab, qr.z, s_lut3, s_lut2);
+			rgb_tables_prepend(left, ql.y, s_lut3, s_lut2);
+			rgb_tables_prepend(tab, qr.y, s_lut3, s_lut2);
+			rgb_tables_prepend(left, ql.x, s_lut3, s_lut2);
+			rgb_tables_prepend(tab, qr.x, s_lut3, s_lut2);
+			asum += (ql.x >> 24) + (ql.y >> 24) + (ql.z >> 24) + (ql.w >> 24) + (qr.x >> 24) + (qr.y >> 24) + (qr.z >> 24) + (qr.w >> 24);
 		}
-		cur ^= 1;
-		__syncthreads();
+		RgbTables whole;
+		rgb_tables_join(whole, left, tab);
+		tab = whole;
+	} else if (srccomps == 4) {
+		const uint32_t *p = reinterpret_cast<const uint32_t *>(src) + first;
+		for (int i = count; i > 0; --i) {
+			const uint32_t w = __ldg(p + i - 1);
+			rgb_tables_prepend(tab, w, s_lut3, s_lut2);
+			asum += w >> 24;
+		}
+	} else {
+		const uint8_t *p = src + first * 3;
+		for (int i = count; i > 0; --i) {
+			const uint8_t *q = p + (size_t) (i - 1) * 3;
+			rgb_tables_prepend(tab, (uint32_t) __ldg(q) | ((uint32_t) __ldg(q + 1) << 8) | ((uint32_t) __ldg(q + 2) << 16),
+					s_lut3, s_lut2);
+		}
 	}
-	const CarryMap *incl = buf + cur * kTileThreads * 4;
+	ByteMap m[4];
+	rgb_tables_store(tab, m[0], m[1], m[2]);
+	if (kinds.k[3] == kChanShift4)
+		alpha_map_of_run(m[3], kChanShift4, src + first * 4 + 3, 4, count); // DXT3 only: 31 explicit trajectories
+	else {
+#pragma unroll
+		for (int k = 0; k < 32; ++k)
+			m[3].e[k] = 0;
+		m[3].e[0] = (uint8_t) (asum % 255u); // diffuse1: the carry is a running sum mod 255
+	}
 	const size_t chunk = (size_t) blockIdx.x * kTileThreads + t;
 #pragma unroll
 	for (int ch = 0; ch < 4; ++ch) {
-		CarryMap ex;
-		if (t == 0)
-			map_identity(ex, kinds.k[ch]);
-		else
-			ex = incl[(t - 1) * 4 + ch];
-		prefix[chunk * 4 + ch] = ex;
-		if (t == kTileThreads - 1)
-			tilemaps[(size_t) blockIdx.x * 4 + ch] = incl[t * 4 + ch];
+		chunkmaps[chunk * 4 + ch] = m[ch];
+		s_maps[t][ch] = m[ch];
 	}
+	__syncthreads();
+	// tree reduction: s_maps[t] <- s_maps[t] then s_maps[t + stride]
+	for (int stride = 1; stride < kTileThreads; stride <<= 1) {
+		if ((t & (2 * stride - 1)) == 0) {
+#pragma unroll
+			for (int ch = 0; ch < 4; ++ch) {
+				ByteMap r;
+				bmap_compose(r, s_maps[t][ch], s_maps[t + stride][ch], kinds.k[ch]);
+				s_maps[t][ch] = r;
+			}
+		}
+		__syncthreads();
+	}
+	if (t < 4)
+		tilemaps[(size_t) blockIdx.x * 4 + t] = s_maps[0][t];
 }
 
 // One CTA.  summary == nullptr: carry[] (4 ints) is the carry into tile 0; writes tile_carry[tile][4] and
@@ -147,118 +150,195 @@ dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kind
 constexpr int kScanThreads = 1024;
 
 __global__ void __launch_bounds__(kScanThreads)
-dither_scan_kernel(const CarryMap *__restrict__ tilemaps, size_t ntiles, ChanKinds kinds, int *carry,
-		int *__restrict__ tile_carry, CarryMap *__restrict__ partial /* [kScanThreads][4] */, CarryMap *summary)
+dither_scan_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKinds kinds, int *carry,
+		int *__restrict__ tile_carry, ByteMap *summary)
 {
-	__shared__ int start[kScanThreads][4];
+	extern __shared__ __align__(16) uint8_t s_raw[];
+	ByteMap *partial = reinterpret_cast<ByteMap *>(s_raw);            // [kScanThreads][4]: map of each thread's tiles
+	ByteMap *super = partial + kScanThreads * 4;                      // [32][4]: map of each group of 32 threads
+	int *start = reinterpret_cast<int *>(super + 32 * 4);             // [kScanThreads][4]: carry entering each thread's tiles
+	int *sstart = start + kScanThreads * 4;                           // [32][4]
 	const int t = threadIdx.x;
 	const size_t per = (ntiles + kScanThreads - 1) / kScanThreads;
 	const size_t lo = min(ntiles, (size_t) t * per), hi = min(ntiles, lo + per);
 	for (int ch = 0; ch < 4; ++ch) {
-		CarryMap acc;
-		map_identity(acc, kinds.k[ch]);
-		for (size_t i = lo; i < hi; ++i)
-			map_compose(acc, acc, tilemaps[i * 4 + ch], kinds.k[ch]);
+		ByteMap acc;
+		bmap_identity(acc, kinds.k[ch]);
+		for (size_t i = lo; i < hi; ++i) {
+			ByteMap r = acc;
+			bmap_compose(r, acc, tilemaps[i * 4 + ch], kinds.k[ch]);
+			acc = r;
+		}
 		partial[t * 4 + ch] = acc;
+	}
+	__syncthreads();
+	if (t < 32 * 4) { // one thread per (group of 32 partials, channel)
+		const int grp = t >> 2, ch = t & 3;
+		ByteMap acc;
+		bmap_identity(acc, kinds.k[ch]);
+		for (int i = 0; i < 32; ++i) {
+			ByteMap r = acc;
+			bmap_compose(r, acc, partial[(grp * 32 + i) * 4 + ch], kinds.k[ch]);
+			acc = r;
+		}
+		super[grp * 4 + ch] = acc;
 	}
 	__syncthreads();
 	if (summary) {
 		if (t < 4) {
-			CarryMap acc;
-			map_identity(acc, kinds.k[t]);
-			for (int i = 0; i < kScanThreads; ++i)
-				map_compose(acc, acc, partial[i * 4 + t], kinds.k[t]);
+			ByteMap acc;
+			bmap_identity(acc, kinds.k[t]);
+			for (int i = 0; i < 32; ++i) {
+				ByteMap r = acc;
+				bmap_compose(r, acc, super[i * 4 + t], kinds.k[t]);
+				acc = r;
+			}
 			summary[t] = acc;
 		}
 		return;
 	}
 	if (t < 4) {
 		int c = carry[t];
-		for (int i = 0; i < kScanThreads; ++i) {
-			start[i][t] = c;
-			c = map_apply(partial[i * 4 + t], kinds.k[t], c);
+		for (int i = 0; i < 32; ++i) {
+			sstart[i * 4 + t] = c;
+			c = bmap_apply(super[i * 4 + t], kinds.k[t], c);
 		}
 		carry[t] = c;
 	}
 	__syncthreads();
+	if (t < 32 * 4) {
+		const int grp = t >> 2, ch = t & 3;
+		int c = sstart[grp * 4 + ch];
+		for (int i = 0; i < 32; ++i) {
+			start[(grp * 32 + i) * 4 + ch] = c;
+			c = bmap_apply(partial[(grp * 32 + i) * 4 + ch], kinds.k[ch], c);
+		}
+	}
+	__syncthreads();
 	for (int ch = 0; ch < 4; ++ch) {
-		int c = start[t][ch];
+		int c = start[t * 4 + ch];
 		for (size_t i = lo; i < hi; ++i) {
 			tile_carry[i * 4 + ch] = c;
-			c = map_apply(tilemaps[i * 4 + ch], kinds.k[ch], c);
+			c = bmap_apply(tilemaps[i * 4 + ch], kinds.k[ch], c);
 		}
 	}
 }
 
+constexpr size_t kScanSmem = (size_t) (kScanThreads * 4 + 32 * 4) * sizeof(ByteMap) + (size_t) (kScanThreads * 4 + 32 * 4) * sizeof(int);
+
 __global__ void __launch_bounds__(kTileThreads)
 dither_apply_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits, ChanKinds kinds, size_t npixels,
-		const CarryMap *__restrict__ prefix, const int *__restrict__ tile_carry, uint32_t *__restrict__ out)
+		const ByteMap *__restrict__ chunkmaps, const int *__restrict__ tile_carry, uint32_t *__restrict__ out)
 {
-	extern __shared__ __align__(16) uint32_t tile[];
-	const size_t tile0 = (size_t) blockIdx.x * kTilePixels;
-	load_tile(src, srccomps, npixels, tile0, tile);
-	__syncthreads();
-
+	__shared__ ByteMap s_maps[kTileThreads * 4];
+	__shared__ int s_carry[kTileThreads * 4];
 	const int t = threadIdx.x;
-	const size_t first = tile0 + (size_t) t * kChunk;
-	const int count = first >= npixels ? 0 : (int) min((size_t) kChunk, npixels - first);
-	const size_t chunk = (size_t) blockIdx.x * kTileThreads + t;
-	uint8_t *row = reinterpret_cast<uint8_t *>(tile + t * kTilePitch);
-#pragma unroll
-	for (int ch = 0; ch < 4; ++ch) {
-		const int kind = kinds.k[ch];
-		if (kind == kChanCopy) {
-			if (srccomps != 4) { // constant alpha (ref :1342-1347); the 8-bit copy needs nothing
-				const uint8_t ones = (uint8_t) ((1u << alphabits) - 1u);
-				for (int i = 0; i < count; ++i)
-					row[i * 4 + 3] = ones;
-			}
-			continue;
-		}
-		const int c0 = map_apply(prefix[chunk * 4 + ch], kind, tile_carry[(size_t) blockIdx.x * 4 + ch]);
-		replay_run(kind, c0, row + ch, 4, count, row + ch);
+	{
+		const uint4 *g = reinterpret_cast<const uint4 *>(chunkmaps + (size_t) blockIdx.x * kTileThreads * 4);
+		uint4 *s = reinterpret_cast<uint4 *>(s_maps);
+		for (int i = t; i < kTileThreads * 4 * 2; i += kTileThreads)
+			s[i] = __ldg(g + i);
 	}
 	__syncthreads();
-	for (int k = threadIdx.x; k < kTilePixels; k += kTileThreads) {
-		const size_t p = tile0 + k;
-		if (p < npixels)
-			out[p] = tile[(k / kChunk) * kTilePitch + (k % kChunk)];
+	if (t < 4) { // one lane per channel walks the 128 chunk maps of the tile
+		int c = tile_carry[(size_t) blockIdx.x * 4 + t];
+		const int kind = kinds.k[t];
+		for (int i = 0; i < kTileThreads; ++i) {
+			s_carry[i * 4 + t] = c;
+			c = bmap_apply(s_maps[i * 4 + t], kind, c);
+		}
+	}
+	__syncthreads();
+
+	const size_t first = ((size_t) blockIdx.x * kTileThreads + t) * kChunk;
+	const int count = first >= npixels ? 0 : (int) min((size_t) kChunk, npixels - first);
+	int carry[4] = {s_carry[t * 4 + 0], s_carry[t * 4 + 1], s_carry[t * 4 + 2], s_carry[t * 4 + 3]};
+	const bool has_alpha = srccomps == 4;
+	const int ak = kinds.k[3];
+	if (srccomps == 4 && count == kChunk && (((size_t) src | (size_t) out) & 15) == 0) {
+		// each thread streams its own 512 contiguous bytes: 8 x 128-bit loads in flight, replay, 128-bit stores
+		const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(src) + first);
+		uint4 *o = reinterpret_cast<uint4 *>(out + first);
+		for (int i = 0; i < kChunk / 4; i += 8) {
+			uint4 q[8];
+#pragma unroll
+			for (int j = 0; j < 8; ++j)
+				q[j] = __ldg(p + i + j);
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				q[j].x = replay_texel(carry, q[j].x, ak, true, alphabits);
+				q[j].y = replay_texel(carry, q[j].y, ak, true, alphabits);
+				q[j].z = replay_texel(carry, q[j].z, ak, true, alphabits);
+				q[j].w = replay_texel(carry, q[j].w, ak, true, alphabits);
+				o[i + j] = q[j];
+			}
+		}
+	} else {
+		for (int i = 0; i < count; ++i) {
+			uint32_t w;
+			if (srccomps == 4)
+				w = __ldg(reinterpret_cast<const uint32_t *>(src) + first + i);
+			else {
+				const uint8_t *q = src + (first + i) * 3;
+				w = (uint32_t) __ldg(q) | ((uint32_t) __ldg(q + 1) << 8) | ((uint32_t) __ldg(q + 2) << 16);
+			}
+			out[first + i] = replay_texel(carry, w, ak, has_alpha, alphabits);
+		}
 	}
 }
 
 static size_t dither_tiles(size_t npixels) { return (npixels + kTilePixels - 1) / kTilePixels; }
 
-// workspace: prefix maps [tiles*128][4] | tile maps [tiles][4] | scan partials [1024][4] | tile carries [tiles][4]
+// workspace: chunk maps [tiles*128][4] | tile maps [tiles][4] | tile carries [tiles][4]
 size_t dither_workspace_bytes(size_t npixels)
 {
 	const size_t tiles = dither_tiles(npixels);
-	return (tiles * kTileThreads * 4 + tiles * 4 + (size_t) kScanThreads * 4) * sizeof(CarryMap) + tiles * 4 * sizeof(int) + 64;
+	return (tiles * kTileThreads * 4 + tiles * 4) * sizeof(ByteMap) + tiles * 4 * sizeof(int) + 64;
+}
+
+static const DitherLut *device_dither_lut(cudaError_t *err)
+{
+	// one copy per device, built on first use (host computes 9 KB of selectors from diffuse_step itself)
+	static const DitherLut *per_device[64] = {nullptr};
+	int dev = 0;
+	*err = cudaGetDevice(&dev);
+	if (*err != cudaSuccess || dev < 0 || dev >= 64)
+		return nullptr;
+	if (!per_device[dev]) {
+		static DitherLut host;
+		build_dither_lut(host);
+		DitherLut *d = nullptr;
+		if ((*err = cudaMalloc((void **) &d, sizeof(DitherLut))) != cudaSuccess)
+			return nullptr;
+		if ((*err = cudaMemcpy(d, &host, sizeof(DitherLut), cudaMemcpyHostToDevice)) != cudaSuccess)
+			return nullptr;
+		per_device[dev] = d;
+	}
+	return per_device[dev];
 }
 
 static cudaError_t run_dither(const void *d_src, int srccomps, int alphabits, size_t npixels, void *d_reduced,
-		int *d_carry, CarryMap *d_summary, void *d_workspace, cudaStream_t stream)
+		int *d_carry, ByteMap *d_summary, void *d_workspace, cudaStream_t stream)
 {
 	if (!npixels)
 		return cudaSuccess;
 	const size_t tiles = dither_tiles(npixels);
-	CarryMap *prefix = (CarryMap *) d_workspace;
-	CarryMap *tilemaps = prefix + tiles * kTileThreads * 4;
-	CarryMap *partial = tilemaps + tiles * 4;
-	int *tile_carry = (int *) (partial + (size_t) kScanThreads * 4);
+	ByteMap *chunkmaps = (ByteMap *) d_workspace;
+	ByteMap *tilemaps = chunkmaps + tiles * kTileThreads * 4;
+	int *tile_carry = (int *) (tilemaps + tiles * 4);
 	const ChanKinds kinds = chan_kinds(srccomps, alphabits);
-	const size_t smem = (size_t) kTileThreads * kTilePitch * 4;
-	static_assert((size_t) kTileThreads * kTilePitch * 4 >= 2 * kTileThreads * 4 * sizeof(CarryMap), "scan buffers must fit the tile");
 	cudaError_t e;
-	if ((e = cudaFuncSetAttribute(dither_maps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess)
+	const DitherLut *lut = device_dither_lut(&e);
+	if (!lut)
 		return e;
-	if ((e = cudaFuncSetAttribute(dither_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)) != cudaSuccess)
+	if ((e = cudaFuncSetAttribute(dither_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScanSmem)) != cudaSuccess)
 		return e;
-	dither_maps_kernel<<<(unsigned) tiles, kTileThreads, smem, stream>>>((const uint8_t *) d_src, srccomps, kinds, npixels,
-			prefix, tilemaps);
-	dither_scan_kernel<<<1, kScanThreads, 0, stream>>>(tilemaps, tiles, kinds, d_carry, tile_carry, partial, d_summary);
+	dither_maps_kernel<<<(unsigned) tiles, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, kinds, npixels, lut,
+			chunkmaps, tilemaps);
+	dither_scan_kernel<<<1, kScanThreads, kScanSmem, stream>>>(tilemaps, tiles, kinds, d_carry, tile_carry, d_summary);
 	if (!d_summary)
-		dither_apply_kernel<<<(unsigned) tiles, kTileThreads, smem, stream>>>((const uint8_t *) d_src, srccomps, alphabits,
-				kinds, npixels, prefix, tile_carry, (uint32_t *) d_reduced);
+		dither_apply_kernel<<<(unsigned) tiles, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, alphabits,
+				kinds, npixels, chunkmaps, tile_carry, (uint32_t *) d_reduced);
 	return cudaGetLastError();
 }
 
@@ -268,7 +348,7 @@ cudaError_t launch_prepass_simple(const void *d_src, int srccomps, int alphabits
 	return run_dither(d_src, srccomps, alphabits, npixels, d_reduced, d_carry, nullptr, d_workspace, stream);
 }
 
-cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits, size_t npixels, CarryMap *d_summary,
+cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits, size_t npixels, ByteMap *d_summary,
 		void *d_workspace, cudaStream_t stream)
 {
 	return run_dither(d_src, srccomps, alphabits, npixels, nullptr, nullptr, d_summary, d_workspace, stream);

@@ -5,7 +5,7 @@ Blocks are independent except for two pieces of sequential state of the referenc
     handled inside s2tc_b200_encode_rows_device from the image-level cursor;
   * the DITHER_SIMPLE carry, which runs through the image in raster order: every shard computes the
     transfer function of its own texels (s2tc_b200_dither_summary_device), the shards all-gather these
-    96-byte summaries, and each folds the summaries of the shards before it.
+    128-byte summaries, and each folds the summaries of the shards before it.
 No other communication exists: each GPU writes its own slice of the output.
 """
 from .api import Encoder
@@ -17,7 +17,7 @@ def shard_block_rows(total_block_rows, world, rank):
 
 
 def fold_carry(summaries, rank, comps, alphabits, carry=(0, 0, 0, 0)):
-    """Carry entering shard `rank`, given the transfer-function summaries (12 words each) of all shards."""
+    """Carry entering shard `rank`, given the transfer-function summaries (16 words each) of all shards."""
     carry = list(carry)
     for r in range(rank):
         carry = Encoder.carry_apply(summaries[r], comps, alphabits, carry)

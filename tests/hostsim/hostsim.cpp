@@ -23,7 +23,7 @@ constexpr int kChunk = 128, kTileChunks = 128;      // mirrors kernels_misc.cu
 constexpr int kBlocksPerRandThread = 32;              // mirrors api.cu
 
 void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, uint32_t *out,
-		int *carry_io = nullptr, CarryMap *summary = nullptr)
+		int *carry_io = nullptr, ByteMap *summary = nullptr)
 {
 	if (dither == kDitherNone) {
 		for (size_t i = 0; i < npix; ++i) {
@@ -32,8 +32,14 @@ void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, 
 		}
 		return;
 	}
-	// DITHER_SIMPLE through the three phases of kernels_misc.cu
-	const int kinds[4] = {kChanShift3, kChanShift2, kChanShift3, alpha_chan_kind(comps, abits)};
+	// DITHER_SIMPLE through the three phases of kernels_misc.cu (same chunking, same map arithmetic)
+	const ChanKinds kinds = chan_kinds(comps, abits);
+	static DitherLut lut;
+	static bool lut_ready = false;
+	if (!lut_ready) {
+		build_dither_lut(lut);
+		lut_ready = true;
+	}
 	std::vector<uint32_t> wide(npix);
 	for (size_t i = 0; i < npix; ++i) {
 		const uint8_t *p = src + i * comps;
@@ -41,29 +47,57 @@ void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, 
 	}
 	const size_t nchunks = (npix + kChunk - 1) / kChunk;
 	const size_t ntiles = (nchunks + kTileChunks - 1) / kTileChunks;
-	std::vector<CarryMap> prefix(ntiles * kTileChunks * 4), tilemap(ntiles * 4);
-	for (size_t t = 0; t < ntiles; ++t) {
-		CarryMap run[4];
-		for (int ch = 0; ch < 4; ++ch)
-			map_identity(run[ch], kinds[ch]);
-		for (int k = 0; k < kTileChunks; ++k) {
-			const size_t chunk = t * kTileChunks + k, first = chunk * kChunk;
-			const int count = first >= npix ? 0 : (int) std::min<size_t>(kChunk, npix - first);
-			for (int ch = 0; ch < 4; ++ch) {
-				prefix[chunk * 4 + ch] = run[ch];
-				CarryMap m;
-				map_of_run(m, kinds[ch], (const uint8_t *) (wide.data() + (count ? first : 0)) + ch, 4, count);
-				map_compose(run[ch], run[ch], m, kinds[ch]);
+	std::vector<ByteMap> chunkmap(ntiles * kTileChunks * 4), tilemap(ntiles * 4);
+	for (size_t chunk = 0; chunk < ntiles * kTileChunks; ++chunk) { // phase 1: right-to-left PRMT composition
+		const size_t first = chunk * kChunk;
+		const int count = first >= npix ? 0 : (int) std::min<size_t>(kChunk, npix - first);
+		RgbTables tab;
+		rgb_tables_init(tab);
+		uint32_t asum = 0;
+		for (int i = 0; i < count; ++i)
+			asum += wide[first + i] >> 24;
+		if (count == kChunk) { // full chunks: two halves built independently and joined, as the kernel does
+			RgbTables left;
+			rgb_tables_init(left);
+			for (int i = kChunk / 2; i > 0; --i) {
+				rgb_tables_prepend(left, wide[first + i - 1], lut.lut3, lut.lut2);
+				rgb_tables_prepend(tab, wide[first + kChunk / 2 + i - 1], lut.lut3, lut.lut2);
 			}
+			RgbTables whole;
+			rgb_tables_join(whole, left, tab);
+			tab = whole;
+		} else {
+			for (int i = count; i > 0; --i)
+				rgb_tables_prepend(tab, wide[first + i - 1], lut.lut3, lut.lut2);
 		}
-		for (int ch = 0; ch < 4; ++ch)
-			tilemap[t * 4 + ch] = run[ch];
+		ByteMap *m = &chunkmap[chunk * 4];
+		rgb_tables_store(tab, m[0], m[1], m[2]);
+		if (kinds.k[3] == kChanShift4)
+			alpha_map_of_run(m[3], kChanShift4, (const uint8_t *) (wide.data() + (count ? first : 0)) + 3, 4, count);
+		else {
+			memset(m[3].e, 0, sizeof(m[3].e));
+			m[3].e[0] = (uint8_t) (asum % 255u);
+		}
 	}
+	for (size_t t = 0; t < ntiles; ++t)
+		for (int ch = 0; ch < 4; ++ch) {
+			ByteMap acc;
+			bmap_identity(acc, kinds.k[ch]);
+			for (int k = 0; k < kTileChunks; ++k) {
+				ByteMap r = acc;
+				bmap_compose(r, acc, chunkmap[(t * kTileChunks + k) * 4 + ch], kinds.k[ch]);
+				acc = r;
+			}
+			tilemap[t * 4 + ch] = acc;
+		}
 	if (summary) { // transfer function of the whole range = composition of the tile maps
 		for (int ch = 0; ch < 4; ++ch) {
-			map_identity(summary[ch], kinds[ch]);
-			for (size_t t = 0; t < ntiles; ++t)
-				map_compose(summary[ch], summary[ch], tilemap[t * 4 + ch], kinds[ch]);
+			bmap_identity(summary[ch], kinds.k[ch]);
+			for (size_t t = 0; t < ntiles; ++t) {
+				ByteMap r = summary[ch];
+				bmap_compose(r, summary[ch], tilemap[t * 4 + ch], kinds.k[ch]);
+				summary[ch] = r;
+			}
 		}
 		return;
 	}
@@ -71,26 +105,23 @@ void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, 
 	if (carry_io)
 		memcpy(carry, carry_io, sizeof(carry));
 	std::vector<int> tile_carry(ntiles * 4);
-	for (size_t t = 0; t < ntiles; ++t)
+	for (size_t t = 0; t < ntiles; ++t) // phase 2
 		for (int ch = 0; ch < 4; ++ch) {
 			tile_carry[t * 4 + ch] = carry[ch];
-			carry[ch] = map_apply(tilemap[t * 4 + ch], kinds[ch], carry[ch]);
+			carry[ch] = bmap_apply(tilemap[t * 4 + ch], kinds.k[ch], carry[ch]);
 		}
 	if (carry_io)
 		memcpy(carry_io, carry, sizeof(carry));
-	for (size_t chunk = 0; chunk < nchunks; ++chunk) {
-		const size_t first = chunk * kChunk;
-		const int count = (int) std::min<size_t>(kChunk, npix - first);
-		uint8_t *row = (uint8_t *) (wide.data() + first);
-		for (int ch = 0; ch < 4; ++ch) {
-			if (kinds[ch] == kChanCopy) {
-				if (comps != 4)
-					for (int i = 0; i < count; ++i)
-						row[i * 4 + 3] = (uint8_t) ((1u << abits) - 1u);
-				continue;
-			}
-			const int c0 = map_apply(prefix[chunk * 4 + ch], kinds[ch], tile_carry[(chunk / kTileChunks) * 4 + ch]);
-			replay_run(kinds[ch], c0, row + ch, 4, count, row + ch);
+	for (size_t t = 0; t < ntiles; ++t) { // phase 3: walk the chunk maps, replay every chunk
+		int c[4] = {tile_carry[t * 4], tile_carry[t * 4 + 1], tile_carry[t * 4 + 2], tile_carry[t * 4 + 3]};
+		for (int k = 0; k < kTileChunks; ++k) {
+			const size_t chunk = t * kTileChunks + k, first = chunk * kChunk;
+			const int count = first >= npix ? 0 : (int) std::min<size_t>(kChunk, npix - first);
+			int cc[4] = {c[0], c[1], c[2], c[3]};
+			for (int i = 0; i < count; ++i)
+				wide[first + i] = replay_texel(cc, wide[first + i], kinds.k[3], comps == 4, abits);
+			for (int ch = 0; ch < 4; ++ch)
+				c[ch] = bmap_apply(chunkmap[chunk * 4 + ch], kinds.k[ch], c[ch]);
 		}
 	}
 	memcpy(out, wide.data(), npix * 4);
@@ -210,13 +241,13 @@ void hostsim_prepass_range(int srccomps, int abits, size_t npix, const uint8_t *
 	prepass(src, srccomps == 3 ? 3 : 4, abits, kDitherSimple, npix, (uint32_t *) out, carry_io);
 }
 
-// the range's transfer function: 4 channels x 3 words, the layout s2tc_b200_dither_summary_device returns
+// the range's transfer function: 4 channels x 32 bytes, the layout s2tc_b200_dither_summary_device returns
 void hostsim_dither_summary(int srccomps, int abits, size_t npix, const uint8_t *src, uint64_t *maps)
 {
-	CarryMap m[4];
+	ByteMap m[4];
 	prepass(src, srccomps == 3 ? 3 : 4, abits, kDitherSimple, npix, nullptr, nullptr, m);
 	for (int ch = 0; ch < 4; ++ch)
-		memcpy(maps + 3 * ch, m[ch].w, sizeof(m[ch].w));
+		memcpy(maps + 4 * ch, m[ch].e, sizeof(m[ch].e));
 }
 
 void hostsim_transcode(int dxt, uint8_t *blocks, size_t nblocks)
