@@ -143,88 +143,101 @@ dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kind
 		tilemaps[(size_t) blockIdx.x * 4 + t] = s_maps[0][t];
 }
 
-// One CTA.  summary == nullptr: carry[] (4 ints) is the carry into tile 0; writes tile_carry[tile][4] and
-// leaves the carry out of the last tile in carry[].  summary != nullptr: writes the composed maps of all
-// tiles instead (the "transfer function" of this texel range, exchanged between GPUs when a carry
-// chain is sharded).
+// One CTA of 32 warps.  A warp holds a map with entry k in lane k, so composing two maps is ONE shuffle
+// (out[k] = second[first[k]] = shfl(second, first)) and applying a map to a carry is a broadcast shuffle.
+// summary == nullptr: carry[] (4 ints) is the carry into tile 0; writes tile_carry[tile][4] and leaves the
+// carry out of the last tile in carry[].  summary != nullptr: writes the composed maps of all tiles instead
+// (the "transfer function" of this texel range, exchanged between GPUs when a carry chain is sharded).
 constexpr int kScanThreads = 1024;
+
+__device__ __forceinline__ int scan_lookup(int kind, int table_byte, int state_index)
+{
+	// shift kinds: entry `state_index` of the map whose entry k sits in lane k; bit1: (sum so far + sum) mod 255
+	if (kind == kChanBit1)
+		return (state_index + __shfl_sync(0xFFFFFFFFu, table_byte, 0)) % 255;
+	return __shfl_sync(0xFFFFFFFFu, table_byte, state_index & 31);
+}
 
 __global__ void __launch_bounds__(kScanThreads)
 dither_scan_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKinds kinds, int *carry,
 		int *__restrict__ tile_carry, ByteMap *summary)
 {
-	extern __shared__ __align__(16) uint8_t s_raw[];
-	ByteMap *partial = reinterpret_cast<ByteMap *>(s_raw);            // [kScanThreads][4]: map of each thread's tiles
-	ByteMap *super = partial + kScanThreads * 4;                      // [32][4]: map of each group of 32 threads
-	int *start = reinterpret_cast<int *>(super + 32 * 4);             // [kScanThreads][4]: carry entering each thread's tiles
-	int *sstart = start + kScanThreads * 4;                           // [32][4]
-	const int t = threadIdx.x;
-	const size_t per = (ntiles + kScanThreads - 1) / kScanThreads;
-	const size_t lo = min(ntiles, (size_t) t * per), hi = min(ntiles, lo + per);
-	for (int ch = 0; ch < 4; ++ch) {
-		ByteMap acc;
-		bmap_identity(acc, kinds.k[ch]);
-		for (size_t i = lo; i < hi; ++i) {
-			ByteMap r = acc;
-			bmap_compose(r, acc, tilemaps[i * 4 + ch], kinds.k[ch]);
-			acc = r;
+	__shared__ uint8_t s_part[32][4][32]; // map of each warp's tiles
+	__shared__ int s_start[32][4];        // carry entering each warp's tiles
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const size_t per = (ntiles + 31) / 32;
+	const size_t lo = min(ntiles, (size_t) warp * per), hi = min(ntiles, lo + per);
+
+	// phase A: compose this warp's tile maps; acc[ch] = entry `lane` of the composition (bit1: running sum)
+	int acc[4];
+#pragma unroll
+	for (int ch = 0; ch < 4; ++ch)
+		acc[ch] = kinds.k[ch] == kChanBit1 ? 0 : lane;
+#pragma unroll 4
+	for (size_t i = lo; i < hi; ++i) {
+#pragma unroll
+		for (int ch = 0; ch < 4; ++ch) {
+			const int b = tilemaps[i * 4 + ch].e[lane];
+			if (kinds.k[ch] <= kChanBit1)
+				acc[ch] = scan_lookup(kinds.k[ch], b, acc[ch]);
 		}
-		partial[t * 4 + ch] = acc;
 	}
+#pragma unroll
+	for (int ch = 0; ch < 4; ++ch)
+		s_part[warp][ch][lane] = (uint8_t) acc[ch];
 	__syncthreads();
-	if (t < 32 * 4) { // one thread per (group of 32 partials, channel)
-		const int grp = t >> 2, ch = t & 3;
-		ByteMap acc;
-		bmap_identity(acc, kinds.k[ch]);
-		for (int i = 0; i < 32; ++i) {
-			ByteMap r = acc;
-			bmap_compose(r, acc, partial[(grp * 32 + i) * 4 + ch], kinds.k[ch]);
-			acc = r;
-		}
-		super[grp * 4 + ch] = acc;
-	}
-	__syncthreads();
-	if (summary) {
-		if (t < 4) {
-			ByteMap acc;
-			bmap_identity(acc, kinds.k[t]);
-			for (int i = 0; i < 32; ++i) {
-				ByteMap r = acc;
-				bmap_compose(r, acc, super[i * 4 + t], kinds.k[t]);
-				acc = r;
+
+	if (warp == 0) {
+		if (summary) { // fold the 32 partial maps, entry `lane` per lane
+#pragma unroll
+			for (int ch = 0; ch < 4; ++ch) {
+				const int kind = kinds.k[ch];
+				int v = kind == kChanBit1 ? 0 : lane;
+				if (kind <= kChanBit1)
+					for (int w = 0; w < 32; ++w)
+						v = kind == kChanBit1 ? (v + s_part[w][ch][0]) % 255 : s_part[w][ch][v & 31];
+				const int ns = chan_states(kind);
+				summary[ch].e[lane] = (uint8_t) ((kind == kChanBit1 ? lane == 0 : lane < ns) ? v : 0);
 			}
-			summary[t] = acc;
+		} else if (lane < 4) { // phase B: the carry entering each warp's range
+			const int kind = kinds.k[lane];
+			int c = carry[lane];
+			for (int w = 0; w < 32; ++w) {
+				s_start[w][lane] = c;
+				if (kind == kChanBit1)
+					c = balanced255(c + s_part[w][lane][0]);
+				else if (kind <= kChanShift4)
+					c = (int) s_part[w][lane][c + chan_radius(kind)] - chan_radius(kind);
+				else
+					c = 0;
+			}
+			carry[lane] = c;
 		}
+	}
+	if (summary)
 		return;
-	}
-	if (t < 4) {
-		int c = carry[t];
-		for (int i = 0; i < 32; ++i) {
-			sstart[i * 4 + t] = c;
-			c = bmap_apply(super[i * 4 + t], kinds.k[t], c);
-		}
-		carry[t] = c;
-	}
 	__syncthreads();
-	if (t < 32 * 4) {
-		const int grp = t >> 2, ch = t & 3;
-		int c = sstart[grp * 4 + ch];
-		for (int i = 0; i < 32; ++i) {
-			start[(grp * 32 + i) * 4 + ch] = c;
-			c = bmap_apply(partial[(grp * 32 + i) * 4 + ch], kinds.k[ch], c);
-		}
-	}
-	__syncthreads();
-	for (int ch = 0; ch < 4; ++ch) {
-		int c = start[t * 4 + ch];
-		for (size_t i = lo; i < hi; ++i) {
-			tile_carry[i * 4 + ch] = c;
-			c = bmap_apply(tilemaps[i * 4 + ch], kinds.k[ch], c);
+
+	// phase C: walk this warp's tiles from its carry; the carry is uniform across the warp
+	int c[4];
+#pragma unroll
+	for (int ch = 0; ch < 4; ++ch)
+		c[ch] = s_start[warp][ch];
+#pragma unroll 4
+	for (size_t i = lo; i < hi; ++i) {
+		if (lane < 4)
+			tile_carry[i * 4 + lane] = lane == 0 ? c[0] : (lane == 1 ? c[1] : (lane == 2 ? c[2] : c[3]));
+#pragma unroll
+		for (int ch = 0; ch < 4; ++ch) {
+			const int kind = kinds.k[ch];
+			const int b = tilemaps[i * 4 + ch].e[lane];
+			if (kind == kChanBit1)
+				c[ch] = balanced255(c[ch] + __shfl_sync(0xFFFFFFFFu, b, 0));
+			else if (kind <= kChanShift4)
+				c[ch] = __shfl_sync(0xFFFFFFFFu, b, c[ch] + chan_radius(kind)) - chan_radius(kind);
 		}
 	}
 }
-
-constexpr size_t kScanSmem = (size_t) (kScanThreads * 4 + 32 * 4) * sizeof(ByteMap) + (size_t) (kScanThreads * 4 + 32 * 4) * sizeof(int);
 
 __global__ void __launch_bounds__(kTileThreads)
 dither_apply_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits, ChanKinds kinds, size_t npixels,
@@ -331,11 +344,9 @@ static cudaError_t run_dither(const void *d_src, int srccomps, int alphabits, si
 	const DitherLut *lut = device_dither_lut(&e);
 	if (!lut)
 		return e;
-	if ((e = cudaFuncSetAttribute(dither_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kScanSmem)) != cudaSuccess)
-		return e;
 	dither_maps_kernel<<<(unsigned) tiles, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, kinds, npixels, lut,
 			chunkmaps, tilemaps);
-	dither_scan_kernel<<<1, kScanThreads, kScanSmem, stream>>>(tilemaps, tiles, kinds, d_carry, tile_carry, d_summary);
+	dither_scan_kernel<<<1, kScanThreads, 0, stream>>>(tilemaps, tiles, kinds, d_carry, tile_carry, d_summary);
 	if (!d_summary)
 		dither_apply_kernel<<<(unsigned) tiles, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, alphabits,
 				kinds, npixels, chunkmaps, tile_carry, (uint32_t *) d_reduced);

@@ -69,6 +69,15 @@ def test_srgb_wrap_noise(encoder):
         _cmp(encoder, img, dxt, O.SRGB, nr, rf, O.DITHER_NONE)
 
 
+def test_srgb_negative_sums(encoder):
+    """Saturated magenta/green texels: SRGB distances (and pair sums) go negative; both search kernels must
+    follow the reference's acceptance rule."""
+    from test_hostsim import magenta_green
+    img = magenta_green(64, 64, 1)
+    for dxt, nr, rf in itertools.product((O.DXT1, O.DXT3, O.DXT5), (0, 6), (0, 1, 2)):
+        _cmp(encoder, img, dxt, O.SRGB, nr, rf, O.DITHER_NONE, cursor=2)
+
+
 def test_rand_cursor_continuity(encoder):
     """Two consecutive calls continue one rand() stream (mip levels, successive textures)."""
     a = synth.synth_rgba(32, 32, seed=1)
