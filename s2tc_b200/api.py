@@ -13,7 +13,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-_LIBDIR = os.path.join(_HERE, "lib")
+_LIBDIR = os.environ.get("S2TC_B200_LIBDIR") or os.path.join(_HERE, "lib")   # override: A/B builds of the kernels
 
 # enumerators: values of the reference (s2tc_algorithm.h:31-63)
 DITHER_NONE, DITHER_SIMPLE, DITHER_FLOYDSTEINBERG = 0, 1, 2
