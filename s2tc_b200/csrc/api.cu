@@ -146,7 +146,7 @@ int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &
 		return 0;
 	}
 	const int nrandom = s.nrandom > 0 ? s.nrandom : 0;
-	if (nrandom == 0 && !getenv("S2TC_B200_FORCE_GROUP_SEARCH")) { // <= 16 candidates: the fused register-resident encoder
+	if (nrandom == 0) { // <= 16 candidates: the fused register-resident encoder
 		FamScope f(c, st, kFamSearch, 1);
 		CU(launch_encode16(s.dxt, s.cd, s.refine, v, d_dst, st));
 		return 0;

@@ -1,47 +1,45 @@
-// kernels_search.cu -- MODE_NORMAL step 2: the c0/c1 pair search (reference reduce_colors_inplace and
-// reduce_colors_inplace_2fixpoints, s2tc_algorithm.cpp:367-478, reached from :1004-1006), a group of G
-// lanes per 4x4 block.
+// kernels_search.cu -- MODE_NORMAL with random candidates (S2TC_RANDOM_COLORS > 0): the c0/c1 pair search
+// (reference reduce_colors_inplace and reduce_colors_inplace_2fixpoints, s2tc_algorithm.cpp:367-478, reached
+// from :1004-1006), one warp per 4x4 block.
 //
-// Per block the reference builds dists[m][n] (m = gathered colours n <= 16 plus nrandom random
-// candidates) and scans all m(m-1)/2 pairs for the smallest sum_k min(d[i][k], d[j][k]); this is
-// >90 % of its run time for nrandom >= 0.  Here:
-//   * the G lanes of a group gather the block's colours, append the pre-generated random candidates,
-//     cache the per-colour metric features and fill the distance matrix in shared memory,
-//     rows padded to 20 words so that 8 lanes reading 8 consecutive rows with LDS.128 hit 8 distinct
-//     16-byte bank groups;
-//   * row i is held in registers while the lanes stride over j; every lane keeps its first minimum
-//     (strict <, in increasing (i,j) order) and the group merges by (sum, i, j) so that the
-//     reference's "lexicographically first minimum" survives;
-//   * when a sum went negative (only the SRGB metric can wrap) lane 0 replays the
-//     reference's exact acceptance rule "bestsum < 0 || sum < bestsum" over the stored matrix;
-//   * DXT5 repeats the search for alpha with the two fixed points 0 and 255 folded into one extra row.
+// Per block the reference builds dists[m][n] (m = n gathered colours + nrandom random candidates, n <= 16) and
+// scans all m(m-1)/2 pairs for the smallest sum_k min(d[i][k], d[j][k]): 3160 pairs x 16 texels at
+// nrandom = 64, >90 % of its run time.  Here:
+//   * the warp gathers the block's colours, appends the pre-generated random candidates and fills the
+//     distance matrix in shared memory, one row per candidate, columns zero-padded to 16;
+//   * metrics whose distances fit 15 bits (AVG, WAVG, W0AVG <= 20681) and alpha (<= 65025) are stored as
+//     16-bit halves: a row is 8 words, a pair costs 8 VIMNMX.U16x2 and the 16-term sum is formed with
+//     packed three-operand adds (3 x 20681 < 2^16) and three IDP.2A horizontal adds; the other metrics keep
+//     32-bit rows (16 VIMNMX + IADD3 tree);
+//   * the pair triangle is walked in 16x16 tiles: lane (jj, half) keeps row j = 16b+jj of tile column b in
+//     registers and meets rows i = 16a + 8*half + t, t = 0..7, whose loads are warp broadcasts (two distinct
+//     addresses per LDS.128), so shared-memory traffic is ~2 wavefronts per 32 pairs; row pitches (12 / 20
+//     words) make the per-lane row loads conflict-free;
+//   * every lane keeps its minimum by (sum, i, j) and the warp merges lexicographically, which is the
+//     reference's "first minimum in (i, j) order";
+//   * when a sum went negative (only the SRGB metric can wrap) lane 0 replays the reference's
+//     acceptance rule "bestsum < 0 || sum < bestsum" verbatim over the stored matrix;
+//   * DXT5 repeats the search for alpha, the two fixed points 0 and 255 folded into every row
+//     (min(d[i][k], f[k]) is stored, so the pair loop is unchanged).
 // Output: the chosen endpoints, 8 bytes per block; kernels_finish.cu turns them into DXT blocks.
+// History: the first version (32-bit rows, lanes striding j with 70 % utilisation) took 198 ms for the
+// 16.7 M blocks of config 3 (profiles/r01c).
 #include "kernels.cuh"
 
 namespace s2tc {
 
-constexpr int kRowWords = 20; // 16 distances + 4 words of padding
 constexpr int kSearchThreads = 128;
+constexpr int kSearchWarps = kSearchThreads / 32;
+constexpr int kPitch16 = 12; // words per row, 16-bit distances (8 used): 8 consecutive rows -> 8 distinct 16-byte slots
+constexpr int kPitch32 = 20; // words per row, 32-bit distances (16 used)
 
-__host__ __device__ inline size_t search_group_bytes(int mcap, int groups_per_cta)
-{
-	size_t b = 64 + (size_t) mcap * 4 + (size_t) mcap * 12 + (size_t) (mcap + 1) * kRowWords * 4;
-	b = (b + 15) & ~(size_t) 15;
-	if (groups_per_cta > 1)
-		while ((b & 127) != 64) // neighbouring groups start 16 banks apart
-			b += 16;
-	return b;
-}
+template <int CD> struct Packs16 { static constexpr bool value = CD == kAVG || CD == kWAVG || CD == kW0AVG; };
 
-template <int G>
-__device__ __forceinline__ unsigned group_mask()
+__host__ __device__ inline size_t search_warp_bytes(int mcap, bool pack16, bool has_feat)
 {
-	if constexpr (G == 32) {
-		return 0xFFFFFFFFu;
-	} else {
-		const unsigned lane = threadIdx.x & 31u;
-		return ((1u << G) - 1u) << (lane & ~(unsigned) (G - 1));
-	}
+	const size_t rows = (size_t) (mcap + 16) * (pack16 ? kPitch16 : kPitch32) * 4; // +16: tile loads may touch one tile past m
+	size_t b = 64 + rows + (size_t) mcap * 4 + (has_feat ? (size_t) mcap * 12 : 0);
+	return (b + 15) & ~(size_t) 15;
 }
 
 // one texel row of a block as reduced texels (zeros outside the image)
@@ -76,130 +74,162 @@ __device__ __forceinline__ void load_block_row(const ImageView &v, int x0, int y
 	}
 }
 
-// sum_k min(a[k], b[k]) (and a fixed row f for alpha), wrapping like the reference's int accumulate
-template <bool FIXED>
-__device__ __forceinline__ int pair_sum(const int *ri, const int *rowj, const int *rf)
+// ---- sum_k min(a[k], b[k]) over one row pair ----------------------------------------------------------
+// 16-bit halves.  SUM3: every value <= 21845, so three packed words can be added before widening.
+template <bool SUM3>
+__device__ __forceinline__ int pair_sum_p16(const uint32_t (&a)[8], const uint32_t (&b)[8])
 {
-	uint32_t s = 0;
+	uint32_t m[8];
 #pragma unroll
-	for (int q = 0; q < 4; ++q) {
-		const int4 bj = *reinterpret_cast<const int4 *>(rowj + 4 * q);
-		int v0 = min(ri[4 * q + 0], bj.x), v1 = min(ri[4 * q + 1], bj.y);
-		int v2 = min(ri[4 * q + 2], bj.z), v3 = min(ri[4 * q + 3], bj.w);
-		if (FIXED) {
-			v0 = min(v0, rf[4 * q + 0]);
-			v1 = min(v1, rf[4 * q + 1]);
-			v2 = min(v2, rf[4 * q + 2]);
-			v3 = min(v3, rf[4 * q + 3]);
-		}
-		s += (uint32_t) v0 + (uint32_t) v1 + (uint32_t) v2 + (uint32_t) v3;
+	for (int q = 0; q < 8; ++q)
+		m[q] = __vminu2(a[q], b[q]);
+	uint32_t s = 0;
+	if (SUM3) {
+		s = __dp2a_lo(m[0] + m[1] + m[2], 0x0101u, s);
+		s = __dp2a_lo(m[3] + m[4] + m[5], 0x0101u, s);
+		s = __dp2a_lo(m[6] + m[7], 0x0101u, s);
+	} else {
+#pragma unroll
+		for (int q = 0; q < 8; ++q)
+			s = __dp2a_lo(m[q], 0x0101u, s);
 	}
 	return (int) s;
 }
 
-// Scans all pairs i<j<m of the matrix in `dist`; returns (i << 16) | j of the winner in every lane.
-template <int G, bool FIXED, bool MAY_BE_NEGATIVE>
-__device__ __forceinline__ uint32_t scan_pairs(const int *dist, int m, int lane, unsigned gmask)
+__device__ __forceinline__ int pair_sum_32(const int (&a)[16], const int (&b)[16])
 {
-	int best = 0x7FFFFFFF;
-	uint32_t bestij = 1u; // (0,1), the reference's initial besti/bestj
-	bool negative = false;
-	int rf[16];
-	if (FIXED) {
+	uint32_t s[4];
+#pragma unroll
+	for (int q = 0; q < 4; ++q)
+		s[q] = (uint32_t) min(a[4 * q], b[4 * q]) + (uint32_t) min(a[4 * q + 1], b[4 * q + 1]) +
+				((uint32_t) min(a[4 * q + 2], b[4 * q + 2]) + (uint32_t) min(a[4 * q + 3], b[4 * q + 3]));
+	return (int) ((s[0] + s[1]) + (s[2] + s[3]));
+}
+
+template <bool PACK16> struct RowRegs;
+template <> struct RowRegs<true> {
+	uint32_t w[8];
+	__device__ __forceinline__ void load(const uint32_t *rows, int r)
+	{
+		const uint4 a = *reinterpret_cast<const uint4 *>(rows + r * kPitch16), b = *reinterpret_cast<const uint4 *>(rows + r * kPitch16 + 4);
+		w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+	}
+};
+template <> struct RowRegs<false> {
+	int w[16];
+	__device__ __forceinline__ void load(const uint32_t *rows, int r)
+	{
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			const int4 f = *reinterpret_cast<const int4 *>(dist + m * kRowWords + 4 * q);
-			rf[4 * q] = f.x; rf[4 * q + 1] = f.y; rf[4 * q + 2] = f.z; rf[4 * q + 3] = f.w;
+			const int4 a = *reinterpret_cast<const int4 *>(rows + r * kPitch32 + 4 * q);
+			w[4 * q] = a.x; w[4 * q + 1] = a.y; w[4 * q + 2] = a.z; w[4 * q + 3] = a.w;
 		}
 	}
-	for (int i = 0; i + 1 < m; ++i) {
-		int ri[16];
-#pragma unroll
-		for (int q = 0; q < 4; ++q) {
-			const int4 a = *reinterpret_cast<const int4 *>(dist + i * kRowWords + 4 * q);
-			ri[4 * q] = a.x; ri[4 * q + 1] = a.y; ri[4 * q + 2] = a.z; ri[4 * q + 3] = a.w;
-		}
-		for (int j = i + 1 + lane; j < m; j += G) {
-			const int sum = pair_sum<FIXED>(ri, dist + j * kRowWords, rf);
-			if (MAY_BE_NEGATIVE)
-				negative |= sum < 0;
-			if (sum < best) {
-				best = sum;
-				bestij = ((uint32_t) i << 16) | (uint32_t) j;
+};
+
+// Scans all pairs i < j < m of the matrix in `rows`; returns (i << 16) | j of the winner in every lane.
+template <bool PACK16, bool SUM3, bool MAY_BE_NEGATIVE>
+__device__ __forceinline__ uint32_t scan_tiles(const uint32_t *rows, int m, int lane)
+{
+	const int jj = lane & 15, half = lane >> 4;
+	const int ntile = (m + 15) >> 4;
+	int best = 0x7FFFFFFF;
+	uint32_t bij = 1u; // (0,1), the reference's initial besti/bestj
+	bool negative = false;
+	for (int b = 0; b < ntile; ++b) {
+		const int j = 16 * b + jj;
+		RowRegs<PACK16> rj;
+		rj.load(rows, j); // rows beyond m are inside the allocation (padding tile) and never accepted
+		for (int a = 0; a <= b; ++a) {
+			const int i0 = 16 * a + 8 * half;
+#pragma unroll 4
+			for (int t = 0; t < 8; ++t) {
+				const int i = i0 + t;
+				RowRegs<PACK16> ri;
+				ri.load(rows, i);
+				int sum;
+				if constexpr (PACK16)
+					sum = pair_sum_p16<SUM3>(ri.w, rj.w);
+				else
+					sum = pair_sum_32(ri.w, rj.w);
+				const uint32_t ij = ((uint32_t) i << 16) | (uint32_t) j;
+				const bool valid = i < j && j < m;
+				if (MAY_BE_NEGATIVE)
+					negative |= valid && sum < 0;
+				if (valid && (sum < best || (sum == best && ij < bij))) {
+					best = sum;
+					bij = ij;
+				}
 			}
 		}
 	}
 #pragma unroll
-	for (int off = G / 2; off > 0; off >>= 1) {
-		const int ob = __shfl_xor_sync(gmask, best, off, G);
-		const uint32_t oij = __shfl_xor_sync(gmask, bestij, off, G);
-		if (ob < best || (ob == best && oij < bestij)) {
+	for (int off = 16; off > 0; off >>= 1) {
+		const int ob = __shfl_xor_sync(0xFFFFFFFFu, best, off);
+		const uint32_t oij = __shfl_xor_sync(0xFFFFFFFFu, bij, off);
+		if (ob < best || (ob == best && oij < bij)) {
 			best = ob;
-			bestij = oij;
+			bij = oij;
 		}
 	}
-	if (MAY_BE_NEGATIVE) {
-		unsigned neg = negative;
-#pragma unroll
-		for (int off = G / 2; off > 0; off >>= 1)
-			neg |= __shfl_xor_sync(gmask, neg, off, G);
-		if (neg) { // rare: replay the reference's rule verbatim on one lane (ref :393-410)
+	if (MAY_BE_NEGATIVE) { // 32-bit rows only
+		if (__any_sync(0xFFFFFFFFu, negative)) { // rare: replay the reference's rule verbatim on one lane (ref :393-410)
 			if (lane == 0) {
 				int bestsum = -1;
-				bestij = 1u;
+				bij = 1u;
 				for (int i = 0; i < m; ++i)
 					for (int j = i + 1; j < m; ++j) {
 						uint32_t s = 0;
 						for (int k = 0; k < 16; ++k)
-							s += (uint32_t) min(dist[i * kRowWords + k], dist[j * kRowWords + k]);
+							s += (uint32_t) min((int) rows[i * kPitch32 + k], (int) rows[j * kPitch32 + k]);
 						const int sum = (int) s;
 						if (bestsum < 0 || sum < bestsum) {
 							bestsum = sum;
-							bestij = ((uint32_t) i << 16) | (uint32_t) j;
+							bij = ((uint32_t) i << 16) | (uint32_t) j;
 						}
 					}
 			}
-			bestij = __shfl_sync(gmask, bestij, 0, G);
+			bij = __shfl_sync(0xFFFFFFFFu, bij, 0);
 		}
 	}
-	return bestij;
+	return bij;
 }
 
-template <int DXT, int CD, int G>
+template <int DXT, int CD>
 __global__ void __launch_bounds__(kSearchThreads)
-pair_search_kernel(ImageView v, int nrandom, int mcap, size_t group_bytes, const uint16_t *__restrict__ cand_c,
+pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, const uint16_t *__restrict__ cand_c,
 		const uint8_t *__restrict__ cand_a, uint2 *__restrict__ ends)
 {
 	typedef Metric<CD> M;
 	typedef typename M::Feat Feat;
+	constexpr bool kPack = Packs16<CD>::value;
+	constexpr int kPitch = kPack ? kPitch16 : kPitch32;
 	extern __shared__ __align__(16) uint8_t smem[];
-	constexpr int kGroups = kSearchThreads / G;
-	const int gi = threadIdx.x / G, lane = threadIdx.x % G;
+	const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int nblocks = v.blocks_w * v.blocks_h;
-	const int t = blockIdx.x * kGroups + gi;
+	const int t = blockIdx.x * kSearchWarps + wi;
 	if (t >= nblocks)
 		return;
-	const unsigned gmask = group_mask<G>();
 
-	uint8_t *gbase = smem + (size_t) gi * group_bytes;
-	uint32_t *px = reinterpret_cast<uint32_t *>(gbase);         // [16]
-	int *dist = reinterpret_cast<int *>(gbase + 64);            // [(mcap+1)][kRowWords]
-	uint32_t *col = reinterpret_cast<uint32_t *>(gbase + 64 + (size_t) (mcap + 1) * kRowWords * 4); // [mcap]
-	Feat *feat = reinterpret_cast<Feat *>(col + mcap);          // [mcap]
+	uint8_t *wbase = smem + (size_t) wi * warp_bytes;
+	uint32_t *px = reinterpret_cast<uint32_t *>(wbase);                                     // [16]
+	uint32_t *rows = reinterpret_cast<uint32_t *>(wbase + 64);                              // [(mcap+16)][kPitch]
+	uint32_t *col = rows + (size_t) (mcap + 16) * kPitch;                                   // [mcap]
+	Feat *feat = reinterpret_cast<Feat *>(col + mcap);                                      // [mcap], 32-bit metrics only
 
 	const int by = t / v.blocks_w, bx = t - by * v.blocks_w;
 	const int x0 = bx * 4, y0 = by * 4;
 	const int w = min(4, v.width - x0), h = min(4, v.rows - y0);
 
 	// 1. texels -> shared
-	for (int y = lane; y < 4; y += G) {
+	if (lane < 4) {
 		uint32_t r[4];
-		load_block_row(v, x0, y0 + y, w, r);
+		load_block_row(v, x0, y0 + lane, w, r);
 #pragma unroll
 		for (int x = 0; x < 4; ++x)
-			px[y * 4 + x] = r[x];
+			px[lane * 4 + x] = r[x];
 	}
-	__syncwarp(gmask);
+	__syncwarp();
 
 	// 2. gather in the reference's column-major order (ref :940-959); bit o = x*4+y
 	const uint32_t valid = valid_mask(w, h);
@@ -214,110 +244,108 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t group_bytes, const
 			usemask |= 1u << ((i & 3) * 4 + (i >> 2));
 	}
 	int n = __popc(usemask);
-	for (int o = lane; o < 16; o += G)
-		if ((usemask >> o) & 1u)
-			col[__popc(usemask & ((1u << o) - 1u))] = px[(o & 3) * 4 + (o >> 2)];
+	if (lane < 16 && ((usemask >> lane) & 1u))
+		col[__popc(usemask & ((1u << lane) - 1u))] = px[(lane & 3) * 4 + (lane >> 2)];
 	if (n == 0) {
 		if (lane == 0)
 			col[0] = 0;
 		n = 1;
 	}
-	int m = n;
-	if (nrandom > 0) { // ref :962-993, candidates pre-generated by kernels_misc.cu
+	{ // ref :962-993, candidates pre-generated by random_candidates_kernel
 		const size_t cb = (size_t) t * nrandom;
-		for (int k = lane; k < nrandom; k += G) {
+		for (int k = lane; k < nrandom; k += 32) {
 			uint32_t c = from565(cand_c[cb + k]);
 			if (DXT == kDxt5)
 				c |= (uint32_t) cand_a[cb + k] << 24;
 			col[n + k] = c;
 		}
-		m = n + nrandom;
 	}
-	__syncwarp(gmask);
-	if (nrandom <= 0 && n == 1) { // ref :997-1001
-		if (lane == 0)
-			col[1] = col[0];
-		m = n = 2;
-		__syncwarp(gmask);
+	const int m = n + nrandom;
+	const int mpad = (m + 15) & ~15; // rows of the last tile beyond m are zero-filled
+	__syncwarp();
+
+	// 3. distance matrix, columns zero-padded to 16 (ref :375-392; argument order matters for SRGB)
+	if constexpr (!kPack) {
+		for (int i = lane; i < m; i += 32)
+			feat[i] = M::feat(col[i]);
+		__syncwarp();
 	}
-
-	// 3. per-colour features
-	for (int i = lane; i < m; i += G)
-		feat[i] = M::feat(col[i]);
-	__syncwarp(gmask);
-
-	// 4. distance matrix, rows zero-padded to 16 (ref :375-392; argument order matters for SRGB)
-	for (int e = lane; e < m * 16; e += G) {
+	for (int e = lane; e < mpad * 16; e += 32) {
 		const int i = e >> 4, k = e & 15;
 		int d = 0;
-		if (k < n && k != i) {
-			if (i < n && k < i)
-				d = M::dist(feat[k], feat[i]);
-			else
-				d = M::dist(feat[i], feat[k]);
+		if (i < m && k < n && k != i) {
+			if constexpr (kPack) {
+				const Feat fi = M::feat(col[i]), fk = M::feat(col[k]);
+				d = M::dist(fi, fk); // symmetric metrics
+			} else {
+				d = (i < n && k < i) ? M::dist(feat[k], feat[i]) : M::dist(feat[i], feat[k]);
+			}
 		}
-		dist[i * kRowWords + k] = d;
+		if constexpr (kPack)
+			reinterpret_cast<uint16_t *>(rows + i * kPitch)[k] = (uint16_t) d;
+		else
+			rows[i * kPitch + k] = (uint32_t) d;
 	}
-	__syncwarp(gmask);
+	__syncwarp();
 
-	// 5. colour pair scan
-	const uint32_t cij = scan_pairs<G, false, M::kMayBeNegative>(dist, m, lane, gmask);
+	// 4. colour pair scan
+	const uint32_t cij = scan_tiles<kPack, true, M::kMayBeNegative>(rows, m, lane);
 	const uint32_t c0 = col[cij >> 16], c1 = col[cij & 0xFFFFu];
 	uint32_t a01 = 0;
 
-	if (DXT == kDxt5) { // ref :416-478
-		__syncwarp(gmask);
-		for (int e = lane; e < (m + 1) * 16; e += G) {
+	if (DXT == kDxt5) { // ref :416-478; alpha rows are always 16-bit, at the 16-bit pitch inside the same buffer
+		__syncwarp();
+		for (int e = lane; e < mpad * 16; e += 32) {
 			const int i = e >> 4, k = e & 15;
 			int d = 0;
-			if (k < n) {
-				const int ak = (int) (col[k] >> 24);
-				if (i < m) {
-					const int ai = (int) (col[i] >> 24);
-					d = (ai - ak) * (ai - ak);
-				} else {
-					d = min(ak * ak, (255 - ak) * (255 - ak));
-				}
+			if (i < m && k < n) {
+				const int ak = (int) (col[k] >> 24), ai = (int) (col[i] >> 24);
+				d = min((ai - ak) * (ai - ak), min(ak * ak, (255 - ak) * (255 - ak)));
 			}
-			dist[i * kRowWords + k] = d;
+			reinterpret_cast<uint16_t *>(rows + i * kPitch16)[k] = (uint16_t) d;
 		}
-		__syncwarp(gmask);
-		const uint32_t aij = scan_pairs<G, true, false>(dist, m, lane, gmask);
+		__syncwarp();
+		const uint32_t aij = scan_tiles<true, false, false>(rows, m, lane);
 		a01 = (col[aij >> 16] >> 24) | ((col[aij & 0xFFFFu] >> 24) << 8);
 	}
 	if (lane == 0)
 		ends[t] = make_uint2(to565(c0) | (to565(c1) << 16), a01);
 }
 
-template <int DXT, int CD, int G>
-static cudaError_t launch_search_g(int nrandom, const ImageView &v, const uint16_t *cand_c, const uint8_t *cand_a,
+static size_t search_smem(int cd, int nrandom)
+{
+	const bool pack = cd == kAVG || cd == kWAVG || cd == kW0AVG;
+	return search_warp_bytes(16 + nrandom, pack, !pack) * kSearchWarps;
+}
+
+template <int DXT, int CD>
+static cudaError_t launch_search_cd(int nrandom, const ImageView &v, const uint16_t *cand_c, const uint8_t *cand_a,
 		uint2 *ends, cudaStream_t stream)
 {
 	const int nblocks = v.blocks_w * v.blocks_h;
 	if (nblocks == 0)
 		return cudaSuccess;
-	constexpr int kGroups = kSearchThreads / G;
-	const int mcap = 16 + (nrandom > 0 ? nrandom : 0);
-	const size_t gb = search_group_bytes(mcap, kGroups);
-	const size_t smem = gb * kGroups;
-	auto kern = pair_search_kernel<DXT, CD, G>;
+	const int mcap = 16 + nrandom;
+	const size_t wb = search_warp_bytes(mcap, Packs16<CD>::value, !Packs16<CD>::value);
+	const size_t smem = wb * kSearchWarps;
+	auto kern = pair_search_kernel<DXT, CD>;
 	if (smem > 48 * 1024) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 		if (e != cudaSuccess)
 			return e;
 	}
-	const dim3 block(kSearchThreads), grid((nblocks + kGroups - 1) / kGroups);
-	kern<<<grid, block, smem, stream>>>(v, nrandom, mcap, gb, cand_c, cand_a, ends);
+	const dim3 block(kSearchThreads), grid((nblocks + kSearchWarps - 1) / kSearchWarps);
+	kern<<<grid, block, smem, stream>>>(v, nrandom, mcap, wb, cand_c, cand_a, ends);
 	return cudaGetLastError();
 }
 
 int pair_search_max_nrandom()
 {
-	// one 32-lane group... four per CTA; 227 KB of shared memory per CTA
-	int lo = 0, hi = 1 << 16;
+	// the 32-bit layout is the larger one; 227 KB of shared memory per CTA
+	int lo = 0, hi = 1 << 15;
 	while (lo < hi) {
-		int mid = (lo + hi + 1) / 2;
-		if (search_group_bytes(16 + mid, kSearchThreads / 32) * (kSearchThreads / 32) <= 227 * 1024)
+		const int mid = (lo + hi + 1) / 2;
+		if (search_smem(kRGB, mid) <= 227 * 1024)
 			lo = mid;
 		else
 			hi = mid - 1;
@@ -325,23 +353,12 @@ int pair_search_max_nrandom()
 	return lo;
 }
 
-template <int DXT, int CD>
-static cudaError_t launch_search_cd(int nrandom, const ImageView &v, const uint16_t *cand_c, const uint8_t *cand_a,
-		uint2 *ends, cudaStream_t stream)
-{
-	// group size: 4 lanes for the 120-pair search of nrandom == 0, a full warp once random
-	// candidates multiply the pair count
-	if (nrandom <= 0)
-		return launch_search_g<DXT, CD, 4>(nrandom, v, cand_c, cand_a, ends, stream);
-	if (nrandom > pair_search_max_nrandom())
-		return cudaErrorInvalidValue;
-	return launch_search_g<DXT, CD, 32>(nrandom, v, cand_c, cand_a, ends, stream);
-}
-
 template <int DXT>
 static cudaError_t launch_search_dxt(int cd, int nrandom, const ImageView &v, const uint16_t *cand_c,
 		const uint8_t *cand_a, uint2 *ends, cudaStream_t stream)
 {
+	if (nrandom <= 0 || nrandom > pair_search_max_nrandom())
+		return cudaErrorInvalidValue; // nrandom <= 0 is served by the fused 16-candidate encoder (search16.inl)
 	switch (cd) {
 	case kRGB: return launch_search_cd<DXT, kRGB>(nrandom, v, cand_c, cand_a, ends, stream);
 	case kYUV: return launch_search_cd<DXT, kYUV>(nrandom, v, cand_c, cand_a, ends, stream);
