@@ -72,14 +72,14 @@ struct PendingTiming {
 };
 
 constexpr int kPlanRing = 64;
-constexpr int kBlocksPerRandThread = 32;
+constexpr int kBlocksPerRandThread = 8;
 constexpr long long kSlabBlocks = 1 << 20; // MODE_NORMAL works through an image in slabs of at most this many blocks
 
 } // namespace
 
 struct s2tc_b200_ctx {
 	int device = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
 	std::mutex mu;
 	DevBuf src, reduced, out, ends, cand_c, cand_a, dither_ws, plans, small;
 	RandPlan *h_plans = nullptr; // pinned ring
@@ -280,6 +280,8 @@ int s2tc_b200_ctx_create(int device, s2tc_b200_ctx **out)
 	s2tc_b200_ctx *c = new s2tc_b200_ctx();
 	c->device = device;
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+	CU(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
 	CU(cudaHostAlloc((void **) &c->h_plans, sizeof(RandPlan) * kPlanRing, cudaHostAllocDefault));
 	CU(cudaHostAlloc((void **) &c->h_carry, 4 * sizeof(int), cudaHostAllocDefault));
 	CU(cudaHostAlloc((void **) &c->h_summary, 16 * sizeof(uint64_t), cudaHostAllocDefault));
@@ -308,6 +310,8 @@ void s2tc_b200_ctx_destroy(s2tc_b200_ctx *c)
 	cudaFreeHost(c->h_summary);
 	cudaFreeHost(c->h_block);
 	cudaStreamDestroy(c->stream);
+	cudaStreamDestroy(c->copy_in);
+	cudaStreamDestroy(c->copy_out);
 	delete c;
 }
 
@@ -415,22 +419,70 @@ int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int
 
 	CU(c->src.reserve(in_bytes));
 	CU(c->out.reserve(out_bytes));
-	CU(cudaMemcpyAsync(c->src.p, src, in_bytes, cudaMemcpyHostToDevice, st));
-	if (int rc = encode_rows(c, s, comps, width, height, c->src.p, 0, bh, c->out.p, cursor, nullptr, st))
-		return rc;
-
 	// ref s2tc_libtxc_dxtn.cpp:243,261,279: a stride below width*2 (DXT1) / width*4 (DXT3/5) means tight rows
 	const size_t row_bytes = dst_row_stride >= width * (bs / 4) ? (size_t) dst_row_stride : tight;
-	if (row_bytes == tight) {
-		CU(cudaMemcpyAsync(dest, c->out.p, out_bytes, cudaMemcpyDeviceToHost, st));
-		CU(cudaStreamSynchronize(st));
-	} else if (row_bytes > tight) {
-		CU(cudaMemcpy2DAsync(dest, row_bytes, c->out.p, tight, tight, bh, cudaMemcpyDeviceToHost, st));
-		CU(cudaStreamSynchronize(st));
-	} else { // rows overlap in dest (stride between width*bs/4 and the padded width): later rows win, as in the reference
+
+	// Large images go through in slabs of block rows on three streams: while slab s is encoded, slab s+1 is on
+	// its way up and slab s-1 on its way down (PCIe is full duplex), so the call costs about max(copy, kernels)
+	// instead of their sum.  The two pieces of cross-slab state stay on the device: the DITHER_SIMPLE carry
+	// (chained through d_carry on the compute stream) and the rand cursor (closed form per block row).
+	int nslab = (int) (in_bytes >> 25); // ~32 MiB of texels per slab
+	nslab = nslab < 1 ? 1 : (nslab > 16 ? 16 : nslab);
+	if (nslab > bh)
+		nslab = bh;
+	if (row_bytes < tight)
+		nslab = 1; // overlapping destination rows: single ordered copy at the end
+	int *d_carry = nullptr;
+	if (s.dither == kDitherSimple) {
+		d_carry = (int *) c->small.p + 8;
+		CU(cudaMemsetAsync(d_carry, 0, 4 * sizeof(int), st));
+	}
+	std::vector<cudaEvent_t> up(nslab), done(nslab);
+	for (int i = 0; i < nslab; ++i) {
+		CU(cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+	}
+	int rc = 0;
+	for (int i = 0; i < nslab && !rc; ++i) {
+		const int r0 = (int) ((long long) bh * i / nslab), r1 = (int) ((long long) bh * (i + 1) / nslab);
+		const int y0 = r0 * 4, y1 = r1 * 4 < height ? r1 * 4 : height;
+		const size_t off = (size_t) y0 * width * comps, len = (size_t) (y1 - y0) * width * comps;
+		cudaStream_t sin_ = nslab > 1 ? c->copy_in : st, sout = nslab > 1 ? c->copy_out : st;
+		CU(cudaMemcpyAsync((uint8_t *) c->src.p + off, src + off, len, cudaMemcpyHostToDevice, sin_));
+		if (nslab > 1) {
+			CU(cudaEventRecord(up[i], sin_));
+			CU(cudaStreamWaitEvent(st, up[i], 0));
+		}
+		uint8_t *d_out = (uint8_t *) c->out.p + (size_t) r0 * tight;
+		rc = encode_rows(c, s, comps, width, height, (const uint8_t *) c->src.p + off, r0, r1, d_out, cursor, d_carry, st);
+		if (rc)
+			break;
+		if (nslab > 1) {
+			CU(cudaEventRecord(done[i], st));
+			CU(cudaStreamWaitEvent(sout, done[i], 0));
+		}
+		if (row_bytes == tight)
+			CU(cudaMemcpyAsync(dest + (size_t) r0 * tight, d_out, (size_t) (r1 - r0) * tight, cudaMemcpyDeviceToHost, sout));
+		else if (row_bytes > tight)
+			CU(cudaMemcpy2DAsync(dest + (size_t) r0 * row_bytes, row_bytes, d_out, tight, tight, r1 - r0, cudaMemcpyDeviceToHost, sout));
+	}
+	cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaSuccess, e3 = cudaSuccess;
+	if (nslab > 1) {
+		e2 = cudaStreamSynchronize(c->copy_in);
+		e3 = cudaStreamSynchronize(c->copy_out);
+	}
+	for (int i = 0; i < nslab; ++i) {
+		cudaEventDestroy(up[i]);
+		cudaEventDestroy(done[i]);
+	}
+	if (rc)
+		return rc;
+	CU(e1);
+	CU(e2);
+	CU(e3);
+	if (row_bytes < tight) { // rows overlap in dest (stride between width*bs/4 and the padded width): later rows win, as in the reference
 		std::vector<uint8_t> tmp(out_bytes);
-		CU(cudaMemcpyAsync(tmp.data(), c->out.p, out_bytes, cudaMemcpyDeviceToHost, st));
-		CU(cudaStreamSynchronize(st));
+		CU(cudaMemcpy(tmp.data(), c->out.p, out_bytes, cudaMemcpyDeviceToHost));
 		for (int r = 0; r < bh; ++r)
 			memcpy(dest + (size_t) r * row_bytes, tmp.data() + (size_t) r * tight, tight);
 	}

@@ -371,33 +371,134 @@ cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits
 // `blocks_per_thread` consecutive blocks, seeks its private replica to the first draw of its first block
 // with O(log t) polynomial products (glibc_rand.cuh) and then generates sequentially.
 // =====================================================================================================
+// a <- a * b mod (x^31 - x^28 - 1), everything in registers (all indices compile-time)
+__device__ __forceinline__ void poly_mulmod_regs(uint32_t (&a)[kLag], const uint32_t *__restrict__ bsrc)
+{
+	uint32_t b[kLag], t[2 * kLag - 1];
+#pragma unroll
+	for (int j = 0; j < kLag; ++j)
+		b[j] = __ldg(bsrc + j);
+#pragma unroll
+	for (int i = 0; i < 2 * kLag - 1; ++i)
+		t[i] = 0;
+#pragma unroll
+	for (int i = 0; i < kLag; ++i)
+#pragma unroll
+		for (int j = 0; j < kLag; ++j)
+			t[i + j] += a[i] * b[j];
+#pragma unroll
+	for (int i = 2 * kLag - 2; i >= kLag; --i) {
+		t[i - 3] += t[i];
+		t[i - kLag] += t[i];
+	}
+#pragma unroll
+	for (int i = 0; i < kLag; ++i)
+		a[i] = t[i];
+}
+
+// x % len for x < 2^31 with the precomputed m = floor((2^32 - 1) / len): one multiply-high, one correction
+__device__ __forceinline__ int mod_small(uint32_t x, uint32_t len, uint32_t m)
+{
+	uint32_t r = x - __umulhi(x, m) * len;
+	if (r >= len)
+		r -= len;
+	return (int) r;
+}
+
+struct CandBoxFast {
+	int lo[4];
+	uint32_t len[4], rcp[4];
+};
+
+template <int DXT>
+__device__ __forceinline__ void box_of_block(const ImageView &v, int blk, CandBoxFast &bx)
+{
+	const int by = blk / v.blocks_w, bxx = blk - by * v.blocks_w;
+	Block b;
+	load_block(v, bxx, by, b);
+	uint32_t c[16];
+	uint8_t ca[16];
+	const int n = gather_colors<DXT>(b, c, ca);
+	const CandBox box = candidate_box(c, ca, n);
+#pragma unroll
+	for (int ch = 0; ch < 3; ++ch) {
+		bx.lo[ch] = box.lo[ch];
+		bx.len[ch] = (uint32_t) box.len[ch];
+	}
+	bx.lo[3] = box.alo;
+	bx.len[3] = (uint32_t) box.alen;
+#pragma unroll
+	for (int ch = 0; ch < 4; ++ch)
+		bx.rcp[ch] = 0xFFFFFFFFu / bx.len[ch];
+}
+
+// 31 candidates = 93 (DXT5: 124) draws = 3 (4) full turns of the 31-word generator ring, so inside this unit the
+// ring slot and the channel of every draw are compile-time constants and the ring lives in registers.
 template <int DXT>
 __global__ void __launch_bounds__(128)
 random_candidates_kernel(ImageView v, int nrandom, const RandPlan *__restrict__ plan, int blocks_per_thread,
 		uint16_t *__restrict__ cand_c, uint8_t *__restrict__ cand_a)
 {
+	constexpr int kDraws = DXT == kDxt5 ? 4 : 3; // per candidate: r, g, b [, a] (ref :986-990)
 	const int nblocks = v.blocks_w * v.blocks_h;
 	const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
 	const long long b0 = (long long) t * blocks_per_thread;
 	if (b0 >= nblocks)
 		return;
-	GlibcRand rng;
-	rand_plan_seek(*plan, t, rng);
 	const int b1 = (int) min((long long) nblocks, b0 + blocks_per_thread);
-	for (int blk = (int) b0; blk < b1; ++blk) {
-		const int by = blk / v.blocks_w, bx = blk - by * v.blocks_w;
-		Block b;
-		load_block(v, bx, by, b);
-		uint32_t c[16];
-		uint8_t ca[16];
-		const int n = gather_colors<DXT>(b, c, ca);
-		const CandBox box = candidate_box(c, ca, n);
-		const size_t o = (size_t) blk * nrandom;
-		for (int k = 0; k < nrandom; ++k) {
-			const uint32_t p = draw_candidate<DXT>(box, rng);
-			cand_c[o + k] = (uint16_t) to565(p);
-			if (DXT == kDxt5)
-				cand_a[o + k] = (uint8_t) (p >> 24);
+
+	// this thread's window of the rand() stream: x^(cursor of block b0) = start * prod step[j]^(bit j of t)
+	uint32_t w[kLag];
+	{
+		uint32_t a[kLag];
+#pragma unroll
+		for (int i = 0; i < kLag; ++i)
+			a[i] = __ldg(&plan->start.c[i]);
+		unsigned bits = t;
+		for (int j = 0; bits; ++j, bits >>= 1)
+			if (bits & 1u)
+				poly_mulmod_regs(a, plan->step[j].c);
+#pragma unroll
+		for (int s = 0; s < kLag; ++s)
+			w[s] = 0;
+#pragma unroll
+		for (int q = 0; q < 2 * kLag - 1; ++q) { // w[s] = sum_j a[j] * base[s + j]
+			const uint32_t bq = __ldg(&plan->base[q]);
+#pragma unroll
+			for (int j = 0; j < kLag; ++j)
+				if (q - j >= 0 && q - j < kLag)
+					w[q - j] += a[j] * bq;
+		}
+	}
+
+	int blk = (int) b0, k = 0;
+	CandBoxFast box;
+	box_of_block<DXT>(v, blk, box);
+	const long long total = (long long) (b1 - (int) b0) * nrandom; // candidates this thread owes
+	for (long long g0 = 0; g0 < total; g0 += kLag) {
+#pragma unroll
+		for (int c = 0; c < kLag; ++c) { // candidate c of the unit: draws kDraws*c .. kDraws*c + kDraws - 1
+			int comp[4] = {0, 0, 0, 0};
+#pragma unroll
+			for (int ch = 0; ch < kDraws; ++ch) {
+				constexpr int dummy = 0;
+				(void) dummy;
+				const int slot = (kDraws * c + ch) % kLag;
+				const uint32_t val = w[slot] + w[(slot + 28) % kLag];
+				w[slot] = val;
+				comp[ch] = box.lo[ch] + mod_small(val >> 1, box.len[ch], box.rcp[ch]);
+			}
+			if (g0 + c < total) {
+				const size_t o = (size_t) blk * nrandom + k;
+				cand_c[o] = (uint16_t) ((comp[0] << 11) | (comp[1] << 5) | comp[2]);
+				if (DXT == kDxt5)
+					cand_a[o] = (uint8_t) comp[3];
+				if (++k == nrandom) {
+					k = 0;
+					if (++blk < b1)
+						box_of_block<DXT>(v, blk, box);
+				}
+			}
 		}
 	}
 }

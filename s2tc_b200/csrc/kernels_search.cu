@@ -127,7 +127,67 @@ template <> struct RowRegs<false> {
 	}
 };
 
-// Scans all pairs i < j < m of the matrix in `rows`; returns (i << 16) | j of the winner in every lane.
+// rank of pair (i, j), i < j < m, in the reference's lexicographic scan order
+__device__ __forceinline__ int pair_rank(int i, int j, int m) { return i * m - ((i * (i + 1)) >> 1) + (j - i - 1); }
+
+// Fast scan for 16-bit rows whose sums stay below 2^SUMBITS and whose pair count fits the remaining bits:
+// every pair becomes the single key (sum << RANKBITS) | rank, so "first minimum in (i, j) order" is an unsigned
+// min.  Only diagonal tiles (i >= j possible) and the last tile column (j >= m possible) need a validity test.
+template <bool SUM3, int SUMBITS>
+__device__ __forceinline__ uint32_t scan_tiles_keyed(const uint32_t *rows, int m, int lane)
+{
+	constexpr int kRankBits = 32 - SUMBITS;
+	const int jj = lane & 15, half = lane >> 4;
+	const int ntile = (m + 15) >> 4;
+	uint32_t best = 0xFFFFFFFFu;
+	for (int b = 0; b < ntile; ++b) {
+		const int j = 16 * b + jj;
+		RowRegs<true> rj;
+		rj.load(rows, j);
+		const bool jlive = j < m;
+		for (int a = 0; a < b; ++a) { // off-diagonal tiles: every i < j
+			const int i0 = 16 * a + 8 * half;
+			int rank = pair_rank(i0, j, m);
+			uint32_t tbest = 0xFFFFFFFFu;
+#pragma unroll
+			for (int t = 0; t < 8; ++t) {
+				RowRegs<true> ri;
+				ri.load(rows, i0 + t);
+				const uint32_t sum = (uint32_t) pair_sum_p16<SUM3>(ri.w, rj.w);
+				tbest = min(tbest, (sum << kRankBits) + (uint32_t) rank);
+				rank += m - (i0 + t) - 2; // rank(i+1, j) - rank(i, j)
+			}
+			if (jlive)
+				best = min(best, tbest);
+		}
+		{ // diagonal tile: pairs with i < j only
+			const int i0 = 16 * b + 8 * half;
+			int rank = pair_rank(i0, j, m);
+#pragma unroll
+			for (int t = 0; t < 8; ++t) {
+				RowRegs<true> ri;
+				ri.load(rows, i0 + t);
+				const uint32_t sum = (uint32_t) pair_sum_p16<SUM3>(ri.w, rj.w);
+				const uint32_t key = (sum << kRankBits) + (uint32_t) rank;
+				if (i0 + t < j && jlive)
+					best = min(best, key);
+				rank += m - (i0 + t) - 2;
+			}
+		}
+	}
+#pragma unroll
+	for (int off = 16; off > 0; off >>= 1)
+		best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, off));
+	// rank -> (i, j): walk the row starts (m <= 128 rows, uniform across the warp)
+	int rank = (int) (best & ((1u << kRankBits) - 1u)), i = 0;
+	while (rank >= m - 1 - i) {
+		rank -= m - 1 - i;
+		++i;
+	}
+	return ((uint32_t) i << 16) | (uint32_t) (i + 1 + rank);
+}
+
+// Generic scan: any row width, any sum range.  Returns (i << 16) | j of the winner in every lane.
 template <bool PACK16, bool SUM3, bool MAY_BE_NEGATIVE>
 __device__ __forceinline__ uint32_t scan_tiles(const uint32_t *rows, int m, int lane)
 {
@@ -215,7 +275,7 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, const 
 	uint32_t *px = reinterpret_cast<uint32_t *>(wbase);                                     // [16]
 	uint32_t *rows = reinterpret_cast<uint32_t *>(wbase + 64);                              // [(mcap+16)][kPitch]
 	uint32_t *col = rows + (size_t) (mcap + 16) * kPitch;                                   // [mcap]
-	Feat *feat = reinterpret_cast<Feat *>(col + mcap);                                      // [mcap], 32-bit metrics only
+	Feat *feat = reinterpret_cast<Feat *>(col + mcap);                                      // [mcap] features (32-bit metrics) or scaled colours
 
 	const int by = t / v.blocks_w, bx = t - by * v.blocks_w;
 	const int x0 = bx * 4, y0 = by * 4;
@@ -265,31 +325,46 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, const 
 	__syncwarp();
 
 	// 3. distance matrix, columns zero-padded to 16 (ref :375-392; argument order matters for SRGB)
-	if constexpr (!kPack) {
+	if constexpr (kPack) {
+		// AVG / WAVG / W0AVG are sums of squares of integer-weighted channel differences (weights 2,1,2 / 2,2,1 /
+		// 1,1,1): scale the channels once per colour, subtract all three per byte, square-and-add with one IDP.4A
+		constexpr uint32_t wr = CD == kW0AVG ? 1 : 2, wg = CD == kWAVG ? 2 : 1, wb = CD == kAVG ? 2 : 1;
+		uint32_t *cvec = reinterpret_cast<uint32_t *>(feat); // [mcap] scaled colours, bytes < 128
+		for (int i = lane; i < m; i += 32) {
+			const uint32_t c = col[i];
+			cvec[i] = (px_r(c) * wr) | ((px_g(c) * wg) << 8) | ((px_b(c) * wb) << 16);
+		}
+		__syncwarp();
+		for (int e = lane; e < mpad * 16; e += 32) {
+			const int i = e >> 4, k = e & 15;
+			int d = 0;
+			if (i < m && k < n) {
+				// per-byte difference without borrows: bytes of cvec are < 128, so (a | 0x80) - b stays within each byte
+				const uint32_t diff = ((cvec[i] | 0x80808080u) - cvec[k]) ^ 0x80808080u;
+				d = __dp4a((int) diff, (int) diff, 0);
+			}
+			reinterpret_cast<uint16_t *>(rows + i * kPitch)[k] = (uint16_t) d;
+		}
+	} else {
 		for (int i = lane; i < m; i += 32)
 			feat[i] = M::feat(col[i]);
 		__syncwarp();
-	}
-	for (int e = lane; e < mpad * 16; e += 32) {
-		const int i = e >> 4, k = e & 15;
-		int d = 0;
-		if (i < m && k < n && k != i) {
-			if constexpr (kPack) {
-				const Feat fi = M::feat(col[i]), fk = M::feat(col[k]);
-				d = M::dist(fi, fk); // symmetric metrics
-			} else {
+		for (int e = lane; e < mpad * 16; e += 32) {
+			const int i = e >> 4, k = e & 15;
+			int d = 0;
+			if (i < m && k < n && k != i)
 				d = (i < n && k < i) ? M::dist(feat[k], feat[i]) : M::dist(feat[i], feat[k]);
-			}
-		}
-		if constexpr (kPack)
-			reinterpret_cast<uint16_t *>(rows + i * kPitch)[k] = (uint16_t) d;
-		else
 			rows[i * kPitch + k] = (uint32_t) d;
+		}
 	}
 	__syncwarp();
 
 	// 4. colour pair scan
-	const uint32_t cij = scan_tiles<kPack, true, M::kMayBeNegative>(rows, m, lane);
+	uint32_t cij;
+	if (kPack && m <= 128) // sums < 16 * 20681 < 2^19, at most 8128 pairs: (sum, rank) fits one word
+		cij = scan_tiles_keyed<true, 19>(rows, m, lane);
+	else
+		cij = scan_tiles<kPack, true, M::kMayBeNegative>(rows, m, lane);
 	const uint32_t c0 = col[cij >> 16], c1 = col[cij & 0xFFFFu];
 	uint32_t a01 = 0;
 
@@ -305,7 +380,8 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, const 
 			reinterpret_cast<uint16_t *>(rows + i * kPitch16)[k] = (uint16_t) d;
 		}
 		__syncwarp();
-		const uint32_t aij = scan_tiles<true, false, false>(rows, m, lane);
+		// alpha sums < 16 * 65025 < 2^20, up to 4095 pairs (m <= 90) for the keyed scan
+		const uint32_t aij = m <= 90 ? scan_tiles_keyed<false, 20>(rows, m, lane) : scan_tiles<true, false, false>(rows, m, lane);
 		a01 = (col[aij >> 16] >> 24) | ((col[aij & 0xFFFFu] >> 24) << 8);
 	}
 	if (lane == 0)
@@ -315,7 +391,7 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, const 
 static size_t search_smem(int cd, int nrandom)
 {
 	const bool pack = cd == kAVG || cd == kWAVG || cd == kW0AVG;
-	return search_warp_bytes(16 + nrandom, pack, !pack) * kSearchWarps;
+	return search_warp_bytes(16 + nrandom, pack, true) * kSearchWarps;
 }
 
 template <int DXT, int CD>
@@ -326,7 +402,7 @@ static cudaError_t launch_search_cd(int nrandom, const ImageView &v, const uint1
 	if (nblocks == 0)
 		return cudaSuccess;
 	const int mcap = 16 + nrandom;
-	const size_t wb = search_warp_bytes(mcap, Packs16<CD>::value, !Packs16<CD>::value);
+	const size_t wb = search_warp_bytes(mcap, Packs16<CD>::value, true);
 	const size_t smem = wb * kSearchWarps;
 	auto kern = pair_search_kernel<DXT, CD>;
 	if (smem > 48 * 1024) {

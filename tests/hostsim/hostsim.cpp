@@ -20,7 +20,7 @@ using namespace s2tc;
 namespace {
 
 constexpr int kChunk = 128, kTileChunks = 128;      // mirrors kernels_misc.cu
-constexpr int kBlocksPerRandThread = 32;              // mirrors api.cu
+constexpr int kBlocksPerRandThread = 8;               // mirrors api.cu
 
 void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, uint32_t *out,
 		int *carry_io = nullptr, ByteMap *summary = nullptr)
