@@ -177,6 +177,11 @@ def main():
         run_reference_arm(args, wl)
         return
 
+    # stdout carries exactly one JSON line: anything libraries print while initialising (NCCL's version banner,
+    # for one) is sent to stderr instead
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import s2tc_b200
     from s2tc_b200 import Settings
@@ -360,6 +365,8 @@ def main():
         "gpu_launches": launches, "clocks": clocks,
         "checked_blocks_vs_oracle": checked,
     }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -87,6 +87,9 @@ struct s2tc_b200_ctx {
 	int *h_carry = nullptr; // pinned, 4 ints
 	uint64_t *h_summary = nullptr; // pinned, 16 words
 	uint8_t *h_block = nullptr;   // pinned, 64 + 16 bytes for the single-block path
+	const void *maps_src = nullptr; // dither workspace currently holds the maps of this texel range
+	size_t maps_npix = 0;
+	int maps_comps = 0, maps_abits = 0;
 	uint64_t launches = 0;
 	bool profiling = false;
 	double fam_ms[kNumFam] = {0};
@@ -212,8 +215,11 @@ int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int
 			carry = (int *) c->small.p;
 			CU(cudaMemsetAsync(carry, 0, 4 * sizeof(int), st));
 		}
-		FamScope f(c, st, kFamPrepass, 3);
-		CU(launch_prepass_simple(d_src_rows, comps, abits, npix, c->reduced.p, carry, c->dither_ws.p, st));
+		// a summary call on exactly these texels (sharded encodes do one to exchange carries) left their maps behind
+		const bool ready = c->maps_src == d_src_rows && c->maps_npix == npix && c->maps_comps == comps && c->maps_abits == abits;
+		c->maps_src = nullptr;
+		FamScope f(c, st, kFamPrepass, ready ? 2 : 3);
+		CU(launch_prepass_simple(d_src_rows, comps, abits, npix, c->reduced.p, carry, c->dither_ws.p, ready, st));
 		texels = (const uint8_t *) c->reduced.p;
 		fmt = kSrcReduced;
 		texel_bytes = 4;
@@ -383,6 +389,10 @@ int s2tc_b200_dither_summary_device(s2tc_b200_ctx *c, int srccomps, int alphabit
 	{
 		FamScope f(c, st, kFamPrepass, 2);
 		CU(launch_dither_summary(d_src_rows, comps, alphabits, npix, d_sum, c->dither_ws.p, st));
+		c->maps_src = d_src_rows; // encode_rows on the same texels may reuse the maps (same stream order assumed)
+		c->maps_npix = npix;
+		c->maps_comps = comps;
+		c->maps_abits = alphabits;
 	}
 	CU(cudaMemcpyAsync(c->h_summary, d_sum, 4 * sizeof(ByteMap), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
@@ -517,8 +527,9 @@ int s2tc_b200_rgb565_host(s2tc_b200_ctx *c, uint8_t *out, const uint8_t *src, in
 		CU(c->dither_ws.reserve(dither_workspace_bytes(npix)));
 		int *carry = (int *) c->small.p;
 		CU(cudaMemsetAsync(carry, 0, 4 * sizeof(int), st));
+		c->maps_src = nullptr;
 		FamScope f(c, st, kFamPrepass, 3);
-		CU(launch_prepass_simple(c->src.p, comps, abits, npix, c->reduced.p, carry, c->dither_ws.p, st));
+		CU(launch_prepass_simple(c->src.p, comps, abits, npix, c->reduced.p, carry, c->dither_ws.p, false, st));
 	}
 	CU(cudaMemcpyAsync(out, c->reduced.p, npix * 4, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));

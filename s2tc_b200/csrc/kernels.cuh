@@ -135,8 +135,10 @@ cudaError_t launch_prepass_none(const void *d_src, int srccomps, int alphabits, 
 // DITHER_SIMPLE over `npixels` texels in raster order.  d_carry: 4 ints (r,g,b,a) carried in and
 // updated to the carry out.  d_maps: workspace of dither_workspace_bytes(npixels).
 size_t dither_workspace_bytes(size_t npixels);
+// maps_ready: the workspace already holds this range's chunk/tile maps (left by launch_dither_summary on the same
+// texels), so phase 1 is skipped.
 cudaError_t launch_prepass_simple(const void *d_src, int srccomps, int alphabits, size_t npixels, void *d_reduced,
-		int *d_carry, void *d_workspace, cudaStream_t stream);
+		int *d_carry, void *d_workspace, bool maps_ready, cudaStream_t stream);
 // transfer maps only (for sharding a carry chain across GPUs): d_summary receives 4 ByteMaps
 cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits, size_t npixels,
 		ByteMap *d_summary, void *d_workspace, cudaStream_t stream);

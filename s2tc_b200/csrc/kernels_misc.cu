@@ -330,7 +330,8 @@ static const DitherLut *device_dither_lut(cudaError_t *err)
 	return per_device[dev];
 }
 
-static cudaError_t run_dither(const void *d_src, int srccomps, int alphabits, size_t npixels, void *d_reduced,
+// phases: 1 = chunk/tile maps, 2 = scan (+ summary), 4 = apply; any combination, in order
+static cudaError_t run_dither(int phases, const void *d_src, int srccomps, int alphabits, size_t npixels, void *d_reduced,
 		int *d_carry, ByteMap *d_summary, void *d_workspace, cudaStream_t stream)
 {
 	if (!npixels)
@@ -344,25 +345,27 @@ static cudaError_t run_dither(const void *d_src, int srccomps, int alphabits, si
 	const DitherLut *lut = device_dither_lut(&e);
 	if (!lut)
 		return e;
-	dither_maps_kernel<<<(unsigned) tiles, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, kinds, npixels, lut,
-			chunkmaps, tilemaps);
-	dither_scan_kernel<<<1, kScanThreads, 0, stream>>>(tilemaps, tiles, kinds, d_carry, tile_carry, d_summary);
-	if (!d_summary)
+	if (phases & 1)
+		dither_maps_kernel<<<(unsigned) tiles, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, kinds, npixels, lut,
+				chunkmaps, tilemaps);
+	if (phases & 2)
+		dither_scan_kernel<<<1, kScanThreads, 0, stream>>>(tilemaps, tiles, kinds, d_carry, tile_carry, d_summary);
+	if (phases & 4)
 		dither_apply_kernel<<<(unsigned) tiles, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, alphabits,
 				kinds, npixels, chunkmaps, tile_carry, (uint32_t *) d_reduced);
 	return cudaGetLastError();
 }
 
 cudaError_t launch_prepass_simple(const void *d_src, int srccomps, int alphabits, size_t npixels, void *d_reduced,
-		int *d_carry, void *d_workspace, cudaStream_t stream)
+		int *d_carry, void *d_workspace, bool maps_ready, cudaStream_t stream)
 {
-	return run_dither(d_src, srccomps, alphabits, npixels, d_reduced, d_carry, nullptr, d_workspace, stream);
+	return run_dither(maps_ready ? 6 : 7, d_src, srccomps, alphabits, npixels, d_reduced, d_carry, nullptr, d_workspace, stream);
 }
 
 cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits, size_t npixels, ByteMap *d_summary,
 		void *d_workspace, cudaStream_t stream)
 {
-	return run_dither(d_src, srccomps, alphabits, npixels, nullptr, nullptr, d_summary, d_workspace, stream);
+	return run_dither(3, d_src, srccomps, alphabits, npixels, nullptr, nullptr, d_summary, d_workspace, stream);
 }
 
 // =====================================================================================================
