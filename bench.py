@@ -39,7 +39,7 @@ WORKLOADS = {
 DXT = {"DXT1": 0, "DXT3": 1, "DXT5": 2}
 CD = {n: i for i, n in enumerate(["RGB", "YUV", "SRGB", "SRGB_MIXED", "AVG", "WAVG", "W0AVG", "NORMALMAP"])}
 REFINE = {"NEVER": 0, "ALWAYS": 1, "LOOP": 2}
-DITHER = {"NONE": 0, "SIMPLE": 1}
+DITHER = {"NONE": 0, "SIMPLE": 1, "FLOYDSTEINBERG": 2}
 GL = {0: 0x83F1, 1: 0x83F2, 2: 0x83F3}
 
 

@@ -92,6 +92,19 @@ int s2tc_b200_dither_summary_device(s2tc_b200_ctx *ctx, int srccomps, int alphab
 		const void *d_src_rows, int row0, int row1, uint64_t maps[16], void *stream);
 int s2tc_b200_carry_apply(const uint64_t map[4], int channel, int srccomps, int alphabits, int carry_in);
 
+/* ---- whole mip chain of an RGBA8 image on the device (SURVEY "next" N2) -----------------------------------
+ * What the reference tool does per file after the DDS header (s2tc_compress.c:722-733): encode the level with
+ * one tx_compress_dxtn call, halve it with Image_MipReduce32 (:427-493), repeat down to 1x1.  Every level is its own
+ * "call" (the DITHER_SIMPLE carry restarts, the rand cursor continues).  Levels are written back to back, tightly.
+ * _device: d_rgba is overwritten (ping-pong with d_scratch, >= width*height bytes); d_dst holds
+ * s2tc_b200_mipchain_bytes(dxt, width, height) bytes. */
+size_t s2tc_b200_mipchain_bytes(int dxt, int width, int height);
+int s2tc_b200_mip_reduce_device(s2tc_b200_ctx *ctx, const void *d_in, int width, int height, void *d_out, void *stream);
+int s2tc_b200_compress_mipchain_device(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int width, int height, void *d_rgba,
+		void *d_scratch, void *d_dst, uint64_t *rand_cursor, void *stream);
+int s2tc_b200_compress_mipchain_host(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int width, int height, const uint8_t *rgba,
+		uint8_t *dest, uint64_t *rand_cursor);
+
 /* ---- 565 pre-pass only: backs the exported rgb565_image (ref s2tc_algorithm.h:38) ------------- */
 int s2tc_b200_rgb565_host(s2tc_b200_ctx *ctx, uint8_t *out, const uint8_t *src, int width, int height, int srccomps,
 		int alphabits, int dither);
@@ -104,6 +117,10 @@ int s2tc_b200_encode_block_host(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s,
 /* ---- S3TC -> S2TC transcode of nblocks blocks, in place (ref s2tc_from_s3tc.cpp:254-263) ------ */
 int s2tc_b200_transcode_host(s2tc_b200_ctx *ctx, int dxt, uint8_t *blocks, size_t nblocks);
 int s2tc_b200_transcode_device(s2tc_b200_ctx *ctx, int dxt, void *d_blocks, size_t nblocks, void *stream);
+
+/* Settings as tx_compress_dxtn would read them from the S2TC_* environment right now (warnings on stderr for
+ * bad values, as in ref s2tc_libtxc_dxtn.cpp:160-216), for callers of the explicit-settings functions. */
+void s2tc_b200_settings_from_env(int dxt, s2tc_b200_settings *out);
 
 /* ---- process-wide rand() cursor used by the handle-less entry points -------------------------- */
 uint64_t s2tc_b200_rand_cursor_get(void);

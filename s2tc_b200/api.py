@@ -133,6 +133,11 @@ def lib():
     L.s2tc_b200_encode_rows_device.argtypes = [vp, sp, i32, i32, i32, vp, i32, i32, vp, u64, C.POINTER(i32), vp]
     L.s2tc_b200_dither_summary_device.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, C.POINTER(u64), vp]
     L.s2tc_b200_carry_apply.argtypes = [C.POINTER(u64), i32, i32, i32, i32]
+    L.s2tc_b200_mipchain_bytes.argtypes = [i32, i32, i32]
+    L.s2tc_b200_mipchain_bytes.restype = C.c_size_t
+    L.s2tc_b200_mip_reduce_device.argtypes = [vp, vp, i32, i32, vp, vp]
+    L.s2tc_b200_compress_mipchain_device.argtypes = [vp, sp, i32, i32, vp, vp, vp, C.POINTER(u64), vp]
+    L.s2tc_b200_compress_mipchain_host.argtypes = [vp, sp, i32, i32, vp, vp, C.POINTER(u64)]
     L.s2tc_b200_rgb565_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32]
     L.s2tc_b200_encode_block_host.argtypes = [vp, sp, vp, vp, i32, i32, i32, C.POINTER(u64)]
     L.s2tc_b200_transcode_host.argtypes = [vp, i32, vp, C.c_size_t]
@@ -217,6 +222,25 @@ class Encoder:
         if stride == 0 and isinstance(out, np.ndarray):
             out = out[:bh * tight]
         return (out, cur.value) if return_cursor else out
+
+    def compress_mipchain(self, img, settings, cursor=0, return_cursor=False):
+        """img: (H, W, 4) uint8.  Every mip level down to 1x1, encoded back to back (the payload of the DDS file the
+        reference's s2tc_compress writes)."""
+        h, w, comps = img.shape
+        assert comps == 4
+        out = np.zeros(lib().s2tc_b200_mipchain_bytes(settings.dxt, w, h), np.uint8)
+        cur = C.c_uint64(cursor)
+        s = settings.c()
+        _check(lib().s2tc_b200_compress_mipchain_host(self._ctx, C.byref(s), w, h, _addr(np.ascontiguousarray(img)), _addr(out),
+                                                      C.byref(cur)))
+        return (out, cur.value) if return_cursor else out
+
+    def compress_mipchain_device(self, rgba, scratch, dst, width, height, settings, cursor=0, stream=None):
+        cur = C.c_uint64(cursor)
+        s = settings.c()
+        _check(lib().s2tc_b200_compress_mipchain_device(self._ctx, C.byref(s), width, height, _addr(rgba), _addr(scratch), _addr(dst),
+                                                        C.byref(cur), stream))
+        return cur.value
 
     def rgb565_image(self, img, alphabits, dither):
         h, w, comps = img.shape

@@ -81,7 +81,7 @@ struct s2tc_b200_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
 	std::mutex mu;
-	DevBuf src, reduced, out, ends, cand_c, cand_a, dither_ws, plans, small;
+	DevBuf src, reduced, out, ends, cand_c, cand_a, dither_ws, plans, small, mip;
 	RandPlan *h_plans = nullptr; // pinned ring
 	int plan_next = 0;
 	int *h_carry = nullptr; // pinned, 4 ints
@@ -224,7 +224,17 @@ int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int
 		fmt = kSrcReduced;
 		texel_bytes = 4;
 	} else if (s.dither == kDitherFloyd) {
-		return fail(S2TC_B200_EUNSUPPORTED, "S2TC_DITHER_MODE=FLOYDSTEINBERG is not implemented on the device yet");
+		if (row0 != 0 || row1 != bh)
+			return fail(S2TC_B200_EUNSUPPORTED, "DITHER_FLOYDSTEINBERG diffuses error between rows: encode the whole image in one call "
+					"(block rows [%d,%d) of %d requested)", row0, row1, bh);
+		CU(c->reduced.reserve(npix * 4));
+		CU(c->dither_ws.reserve(floyd_workspace_bytes(width, height)));
+		c->maps_src = nullptr;
+		FamScope f(c, st, kFamPrepass, comps == 4 && abits != 8 ? 2 : 1);
+		CU(launch_prepass_floyd(d_src_rows, comps, abits, width, height, c->reduced.p, c->dither_ws.p, st));
+		texels = (const uint8_t *) c->reduced.p;
+		fmt = kSrcReduced;
+		texel_bytes = 4;
 	}
 
 	// MODE_NORMAL goes slab by slab to bound the candidate/endpoint workspaces
@@ -308,7 +318,7 @@ void s2tc_b200_ctx_destroy(s2tc_b200_ctx *c)
 		cudaEventDestroy(p.a);
 		cudaEventDestroy(p.b);
 	}
-	DevBuf *bufs[] = {&c->src, &c->reduced, &c->out, &c->ends, &c->cand_c, &c->cand_a, &c->dither_ws, &c->plans, &c->small};
+	DevBuf *bufs[] = {&c->src, &c->reduced, &c->out, &c->ends, &c->cand_c, &c->cand_a, &c->dither_ws, &c->plans, &c->small, &c->mip};
 	for (DevBuf *b : bufs)
 		b->release();
 	cudaFreeHost(c->h_plans);
@@ -440,8 +450,8 @@ int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int
 	nslab = nslab < 1 ? 1 : (nslab > 16 ? 16 : nslab);
 	if (nslab > bh)
 		nslab = bh;
-	if (row_bytes < tight)
-		nslab = 1; // overlapping destination rows: single ordered copy at the end
+	if (row_bytes < tight || s.dither == kDitherFloyd)
+		nslab = 1; // overlapping destination rows: single ordered copy at the end; Floyd-Steinberg: one 2-D recurrence
 	int *d_carry = nullptr;
 	if (s.dither == kDitherSimple) {
 		d_carry = (int *) c->small.p + 8;
@@ -502,6 +512,96 @@ int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int
 	return 0;
 }
 
+size_t s2tc_b200_mipchain_bytes(int dxt, int width, int height)
+{
+	const int bs = block_bytes(norm_dxt(dxt));
+	size_t total = 0;
+	for (int w = width, h = height; w > 0 && h > 0;) {
+		total += (size_t) ((w + 3) / 4) * ((h + 3) / 4) * bs;
+		if (w == 1 && h == 1)
+			break;
+		w = w > 1 ? w >> 1 : w;
+		h = h > 1 ? h >> 1 : h;
+	}
+	return total;
+}
+
+int s2tc_b200_mip_reduce_device(s2tc_b200_ctx *c, const void *d_in, int width, int height, void *d_out, void *stream)
+{
+	if (!c || !d_in || !d_out || width <= 0 || height <= 0)
+		return fail(S2TC_B200_EINVAL, "bad argument");
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	FamScope f(c, st, kFamPrepass, 1);
+	CU(launch_mip_reduce(d_in, width, height, d_out, st));
+	return 0;
+}
+
+int s2tc_b200_compress_mipchain_device(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int width, int height, void *d_rgba,
+		void *d_scratch, void *d_dst, uint64_t *rand_cursor, void *stream)
+{
+	if (!c || !d_rgba || !d_scratch || !d_dst)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	if (width <= 0 || height <= 0)
+		return fail(S2TC_B200_EINVAL, "bad size %dx%d", width, height);
+	s2tc_b200_settings s;
+	if (int rc = settings_normalise(sin, s))
+		return rc;
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	uint64_t cursor = rand_cursor ? *rand_cursor : 0;
+	const int bs = block_bytes(s.dxt);
+	uint8_t *cur = (uint8_t *) d_rgba, *other = (uint8_t *) d_scratch, *dst = (uint8_t *) d_dst;
+	for (int w = width, h = height;;) { // ref s2tc_compress.c:722-733: one tx_compress_dxtn per level, down to 1x1
+		const int bw = (w + 3) / 4, bh = (h + 3) / 4;
+		if (int rc = encode_rows(c, s, 4, w, h, cur, 0, bh, dst, cursor, nullptr, st))
+			return rc;
+		dst += (size_t) bw * bh * bs;
+		cursor += (uint64_t) bw * bh * draws_per_block(s.dxt, s.nrandom);
+		if (w == 1 && h == 1)
+			break;
+		{
+			FamScope f(c, st, kFamPrepass, 1);
+			CU(launch_mip_reduce(cur, w, h, other, st));
+		}
+		uint8_t *t = cur; cur = other; other = t;
+		w = w > 1 ? w >> 1 : w;
+		h = h > 1 ? h >> 1 : h;
+	}
+	if (rand_cursor)
+		*rand_cursor = cursor;
+	return 0;
+}
+
+int s2tc_b200_compress_mipchain_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int width, int height, const uint8_t *rgba,
+		uint8_t *dest, uint64_t *rand_cursor)
+{
+	if (!c || !rgba || !dest)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	if (width <= 0 || height <= 0)
+		return fail(S2TC_B200_EINVAL, "bad size %dx%d", width, height);
+	const size_t in_bytes = (size_t) width * height * 4;
+	const size_t out_bytes = s2tc_b200_mipchain_bytes(sin ? sin->dxt : 0, width, height);
+	void *d_in, *d_tmp, *d_out;
+	{
+		std::lock_guard<std::mutex> lock(c->mu);
+		CU(cudaSetDevice(c->device));
+		CU(c->src.reserve(in_bytes));
+		CU(c->mip.reserve(in_bytes / 4 + 64));
+		CU(c->out.reserve(out_bytes));
+		d_in = c->src.p; d_tmp = c->mip.p; d_out = c->out.p;
+		CU(cudaMemcpyAsync(d_in, rgba, in_bytes, cudaMemcpyHostToDevice, c->stream));
+	}
+	if (int rc = s2tc_b200_compress_mipchain_device(c, sin, width, height, d_in, d_tmp, d_out, rand_cursor, nullptr))
+		return rc;
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaMemcpyAsync(dest, d_out, out_bytes, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
 int s2tc_b200_rgb565_host(s2tc_b200_ctx *c, uint8_t *out, const uint8_t *src, int width, int height, int srccomps,
 		int alphabits, int dither)
 {
@@ -522,7 +622,10 @@ int s2tc_b200_rgb565_host(s2tc_b200_ctx *c, uint8_t *out, const uint8_t *src, in
 		FamScope f(c, st, kFamPrepass, 1);
 		CU(launch_prepass_none(c->src.p, comps, abits, npix, c->reduced.p, st));
 	} else if (dither == kDitherFloyd) {
-		return fail(S2TC_B200_EUNSUPPORTED, "DITHER_FLOYDSTEINBERG is not implemented on the device yet");
+		CU(c->dither_ws.reserve(floyd_workspace_bytes(width, height)));
+		c->maps_src = nullptr;
+		FamScope f(c, st, kFamPrepass, 2);
+		CU(launch_prepass_floyd(c->src.p, comps, abits, width, height, c->reduced.p, c->dither_ws.p, st));
 	} else {
 		CU(c->dither_ws.reserve(dither_workspace_bytes(npix)));
 		int *carry = (int *) c->small.p;

@@ -289,6 +289,41 @@ S2TC_HD uint32_t replay_texel(int (&carry)[4], uint32_t w, int alpha_kind, bool 
 	return r | (g << 8) | (b << 16) | (a << 24);
 }
 
+// ---- DITHER_FLOYDSTEINBERG (ref :1218-1261, :1350-1412) -----------------------------------------------------
+// One texel of floyd() / floyd1(): `incoming` is the error that reached this texel (thisrow[x+1] in the reference),
+// the four parts go right (e7), down-left (e3), down (e5) and down-right (e1).  12-bit domain; C division
+// truncates toward zero and so does CUDA's.  SHIFT 7 selects the 1-bit variant floyd1().
+struct FloydOut {
+	int q, e7, e3, e5, e1;
+};
+
+template <int SHIFT>
+S2TC_HD FloydOut floyd_texel(int src, int incoming)
+{
+	const int s = ((src << 4) | (src >> 4)) + incoming;
+	int q, back;
+	if (SHIFT == 7) {
+		q = s >= 2048;
+		back = q ? 4095 : 0;
+	} else {
+		constexpr int top = (1 << (8 - (SHIFT == 7 ? 1 : SHIFT))) - 1;
+		q = s >> (SHIFT + 4);
+		q = q < 0 ? 0 : (q > top ? top : q);
+		back = q * 4095 / top;
+	}
+	int err = s - back;
+	FloydOut o;
+	o.q = q;
+	o.e7 = (err * 7 + 8) / 16;
+	err -= o.e7;
+	o.e3 = (err * 3 + 4) / 9;
+	err -= o.e3;
+	o.e5 = (err * 5 + 3) / 6;
+	err -= o.e5;
+	o.e1 = err;
+	return o;
+}
+
 // DITHER_NONE on one texel (ref :1269-1306): raw bytes -> reduced texel word
 S2TC_HD uint32_t reduce_none(uint32_t r, uint32_t g, uint32_t b, uint32_t a, int alphabits, bool has_alpha)
 {

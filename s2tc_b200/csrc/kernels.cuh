@@ -143,6 +143,14 @@ cudaError_t launch_prepass_simple(const void *d_src, int srccomps, int alphabits
 cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits, size_t npixels,
 		ByteMap *d_summary, void *d_workspace, cudaStream_t stream);
 
+// DITHER_FLOYDSTEINBERG over a whole width x height image (a 2-D recurrence: it cannot start in the middle)
+size_t floyd_workspace_bytes(int width, int height);
+cudaError_t launch_prepass_floyd(const void *d_src, int srccomps, int alphabits, int width, int height, void *d_reduced,
+		void *d_workspace, cudaStream_t stream);
+
+// one mip step of an RGBA8 image (w x h -> max(w/2,1) x max(h/2,1)); d_out must not alias d_in
+cudaError_t launch_mip_reduce(const void *d_in, int w, int h, void *d_out, cudaStream_t stream);
+
 // S3TC -> S2TC transcode, in place.
 cudaError_t launch_transcode(int dxt, void *d_blocks, size_t nblocks, cudaStream_t stream);
 

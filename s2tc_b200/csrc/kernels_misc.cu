@@ -560,6 +560,42 @@ cudaError_t launch_transcode(int dxt, void *d_blocks, size_t nblocks, cudaStream
 }
 
 // =====================================================================================================
+// Mip reduction (reference Image_MipReduce32, s2tc_compress.c:427-493, as its mip loop :722-733 uses it):
+// every axis still larger than 1 is halved, odd sizes drop the last row/column, texels are the truncated
+// mean of the 2x2 (or 2x1 / 1x2) source texels per channel.  One thread per output texel, 32-bit loads.
+// =====================================================================================================
+__global__ void mip_reduce_kernel(const uint32_t *__restrict__ in, int w, int h, uint32_t *__restrict__ out, int nw, int nh)
+{
+	const int sx = w > 1 ? 2 : 1, sy = h > 1 ? 2 : 1;
+	const size_t n = (size_t) nw * nh, stride = (size_t) gridDim.x * blockDim.x;
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const int y = (int) (i / nw), x = (int) (i - (size_t) y * nw);
+		const uint32_t *p = in + (size_t) y * sy * w + (size_t) x * sx;
+		const uint32_t a = __ldg(p), b = sx == 2 ? __ldg(p + 1) : 0u;
+		const uint32_t c = sy == 2 ? __ldg(p + w) : 0u, d = (sx == 2 && sy == 2) ? __ldg(p + w + 1) : 0u;
+		const int sh = (sx == 2) + (sy == 2);
+		// two channels per word at a time: bytes 0,2 and bytes 1,3 (sums of four bytes need 10 bits)
+		const uint32_t lo = (a & 0x00FF00FFu) + (b & 0x00FF00FFu) + (c & 0x00FF00FFu) + (d & 0x00FF00FFu);
+		const uint32_t hi = ((a >> 8) & 0x00FF00FFu) + ((b >> 8) & 0x00FF00FFu) + ((c >> 8) & 0x00FF00FFu) + ((d >> 8) & 0x00FF00FFu);
+		out[i] = ((lo >> sh) & 0x00FF00FFu) | (((hi >> sh) & 0x00FF00FFu) << 8);
+	}
+}
+
+cudaError_t launch_mip_reduce(const void *d_in, int w, int h, void *d_out, cudaStream_t stream)
+{
+	const int nw = w > 1 ? w >> 1 : w, nh = h > 1 ? h >> 1 : h;
+	const size_t n = (size_t) nw * nh;
+	if (!n || (nw == w && nh == h))
+		return cudaSuccess;
+	const int threads = 256;
+	size_t blocks = (n + threads - 1) / threads;
+	if (blocks > 148 * 32)
+		blocks = 148 * 32;
+	mip_reduce_kernel<<<(unsigned) blocks, threads, 0, stream>>>((const uint32_t *) d_in, w, h, (uint32_t *) d_out, nw, nh);
+	return cudaGetLastError();
+}
+
+// =====================================================================================================
 // Measurement aid: sustained INT32 min+add issue rate, the denominator for the search kernels' roofline
 // (search modes are bound by the integer pipes, not by HBM).  8 independent chains per
 // thread of exactly the two operations the pair scan is made of (IMNMX + IADD).

@@ -165,6 +165,15 @@ inline const unsigned char *block_at(int row_stride_texels, const unsigned char 
 
 extern "C" {
 
+// the reference's environment parsing as a callable (used by tools that drive the batched API directly)
+void s2tc_b200_settings_from_env(int dxt, s2tc_b200_settings *out)
+{
+	if (!out)
+		return;
+	*out = settings_from_env();
+	out->dxt = dxt;
+}
+
 void tx_compress_dxtn(int srccomps, int width, int height, const unsigned char *srcPixData, unsigned int destformat,
 		unsigned char *dest, int dstRowStride)
 {

@@ -5,7 +5,7 @@
 // libtxc_dxtn.so built from s2tc_b200/csrc).  Encoder settings come from the S2TC_* environment, read
 // by tx_compress_dxtn itself.  Output is byte-identical to the reference tool for the same input
 // (tests/test_gpu_cli.py compares the two).  This file is host plumbing only: every texel is encoded by
-// the library's CUDA kernels through tx_compress_dxtn.
+// the library's CUDA kernels (the whole mip chain on the device; with -l, level by level through tx_compress_dxtn).
 #include <dlfcn.h>
 #include <getopt.h>
 #include <strings.h>
@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/s2tc_b200.h"
 #include "../../include/s2tc_b200_txc_dxtn.h"
 
 typedef void (*compress_fn)(int, int, int, const unsigned char *, unsigned int, unsigned char *, int);
@@ -238,6 +239,24 @@ int main(int argc, char **argv)
 	put32(hdr + 108, 0x00401008);
 	fwrite(hdr, 1, sizeof(hdr), out);
 
+	if (!library) {
+		// our own library: the whole chain stays on the GPU (one upload, every level encoded and halved there,
+		// one download) -- same bytes as the per-level loop below
+		s2tc_b200_settings st;
+		s2tc_b200_settings_from_env(format == S2TC_B200_GL_RGBA_DXT1 ? S2TC_B200_DXT1 : (format == S2TC_B200_GL_RGBA_DXT3 ? S2TC_B200_DXT3 : S2TC_B200_DXT5), &st);
+		s2tc_b200_ctx *ctx = s2tc_b200_default_ctx();
+		std::vector<unsigned char> obuf(s2tc_b200_mipchain_bytes(st.dxt, w, h));
+		uint64_t cursor = s2tc_b200_rand_cursor_get();
+		if (!ctx || s2tc_b200_compress_mipchain_host(ctx, &st, w, h, pic.data(), obuf.data(), &cursor) != 0) {
+			fprintf(stderr, "s2tc_compress: %s\n", s2tc_b200_last_error());
+			return 3;
+		}
+		s2tc_b200_rand_cursor_set(cursor);
+		fwrite(obuf.data(), 1, obuf.size(), out);
+		if (outfile)
+			fclose(out);
+		return 0;
+	}
 	for (;;) {
 		const int bw = (w + 3) / 4, bh = (h + 3) / 4;
 		std::vector<unsigned char> obuf((size_t) bs * bw * bh);

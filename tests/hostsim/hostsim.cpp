@@ -22,6 +22,8 @@ namespace {
 constexpr int kChunk = 128, kTileChunks = 128;      // mirrors kernels_misc.cu
 constexpr int kBlocksPerRandThread = 8;               // mirrors api.cu
 
+int fs_width = 0; // image width for the Floyd-Steinberg walk (the other modes only need the texel count)
+
 void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, uint32_t *out,
 		int *carry_io = nullptr, ByteMap *summary = nullptr)
 {
@@ -29,6 +31,44 @@ void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, 
 		for (size_t i = 0; i < npix; ++i) {
 			const uint8_t *p = src + i * comps;
 			out[i] = reduce_none(p[0], p[1], p[2], comps == 4 ? p[3] : 0, abits, comps == 4);
+		}
+		return;
+	}
+	if (dither == kDitherFloyd) { // sequential walk with the kernel's texel arithmetic and its alpha-seed rule
+		const int w = fs_width, h = (int) (npix / fs_width);
+		std::vector<int> cur(3 * (w + 2)), nxt(3 * (w + 2)), seed(w + 2, 0);
+		for (int y = 0; y < h; ++y) {
+			std::fill(nxt.begin(), nxt.end(), 0);
+			for (int x = 0; x < w; ++x) {
+				const uint8_t *p = src + ((size_t) y * w + x) * comps;
+				uint32_t word = comps == 4 ? ((uint32_t) p[3] << 24) : (((1u << abits) - 1u) << 24);
+				for (int c = 0; c < 3; ++c) {
+					int *tr = cur.data() + c * (w + 2), *dr = nxt.data() + c * (w + 2);
+					if (c == 0 && y == h - 1 && (h & 1))
+						seed[x + 1] = tr[x + 1];
+					const FloydOut o = c == 1 ? floyd_texel<2>(p[c], tr[x + 1]) : floyd_texel<3>(p[c], tr[x + 1]);
+					tr[x + 2] += o.e7; dr[x] += o.e3; dr[x + 1] += o.e5; dr[x + 2] += o.e1;
+					word |= (uint32_t) o.q << (8 * c);
+				}
+				out[(size_t) y * w + x] = word;
+			}
+			if (y == h - 1 && !(h & 1))
+				for (int x = 0; x < w + 2; ++x)
+					seed[x] = nxt[x];
+			cur.swap(nxt);
+		}
+		if (comps == 4 && abits != 8) {
+			std::vector<int> ca(seed), na(w + 2);
+			for (int y = 0; y < h; ++y) {
+				std::fill(na.begin(), na.end(), 0);
+				for (int x = 0; x < w; ++x) {
+					const int a = src[((size_t) y * w + x) * 4 + 3];
+					const FloydOut o = abits == 1 ? floyd_texel<7>(a, ca[x + 1]) : floyd_texel<4>(a, ca[x + 1]);
+					ca[x + 2] += o.e7; na[x] += o.e3; na[x + 1] += o.e5; na[x + 2] += o.e1;
+					out[(size_t) y * w + x] = (out[(size_t) y * w + x] & 0x00FFFFFFu) | ((uint32_t) o.q << 24);
+				}
+				ca.swap(na);
+			}
 		}
 		return;
 	}
@@ -207,12 +247,11 @@ void encode_cd(int cd, const uint32_t *img, int width, int height, int nrandom, 
 
 extern "C" {
 
-// tight output; returns 0 or -1 (FLOYDSTEINBERG is not part of the shared code yet)
+// tight output; returns 0
 int hostsim_compress(int srccomps, int width, int height, const uint8_t *src, int dxt, int cd, int nrandom, int refine,
 		int dither, uint64_t cursor, uint8_t *dest)
 {
-	if (dither == kDitherFloyd)
-		return -1;
+	fs_width = width;
 	const int comps = srccomps == 3 ? 3 : 4;
 	dxt = norm_dxt(dxt);
 	cd = norm_cd(cd);
@@ -230,7 +269,7 @@ int hostsim_compress(int srccomps, int width, int height, const uint8_t *src, in
 int hostsim_prepass(int srccomps, int abits, int dither, size_t npix, const uint8_t *src, uint8_t *out)
 {
 	if (dither == kDitherFloyd)
-		return -1;
+		return -1; // needs the image width: go through hostsim_compress
 	prepass(src, srccomps == 3 ? 3 : 4, abits, dither, npix, (uint32_t *) out);
 	return 0;
 }

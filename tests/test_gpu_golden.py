@@ -18,8 +18,6 @@ GOLDEN = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golde
 def test_golden_encode_vectors(encoder):
     cache = {}
     for rec in GOLDEN["encode"]:
-        if rec["dither"] == 2:
-            continue   # FLOYDSTEINBERG: not on the device yet
         key = (rec["gen"], json.dumps(rec["args"], sort_keys=True))
         if key not in cache:
             cache[key] = getattr(synth, rec["gen"])(**rec["args"])
@@ -30,8 +28,6 @@ def test_golden_encode_vectors(encoder):
 
 def test_golden_prepass_and_transcode(encoder):
     for rec in GOLDEN["prepass"]:
-        if rec["dither"] == 2:
-            continue
         img = synth.synth_noise(rec["width"], rec["height"], seed=rec["seed"])
         out = encoder.rgb565_image(img, rec["alphabits"], rec["dither"])
         assert hashlib.sha256(out.tobytes()).hexdigest() == rec["sha256"], rec

@@ -68,7 +68,7 @@ def test_rand_jump_ahead():
 def test_whole_pipeline_against_oracle():
     imgs = [synth.synth_rgba(40, 28, seed=3), synth.synth_noise(37, 21, seed=4), synth.synth_noise(24, 20, seed=5, comps=3)]
     for img in imgs:
-        for dxt, cd, nr, rf, di in itertools.product((0, 1, 2), range(8), (-1, 0, 5, 37), (0, 1, 2), (0, 1)):
+        for dxt, cd, nr, rf, di in itertools.product((0, 1, 2), range(8), (-1, 0, 5, 37), (0, 1, 2), (0, 1, 2)):
             if (cd + nr + rf + di + dxt) % 3:   # a third of the grid keeps the CPU tier quick
                 continue
             a = H.compress(img, dxt, cd, nr, rf, di, cursor=13)
