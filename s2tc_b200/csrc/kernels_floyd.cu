@@ -67,40 +67,65 @@ __global__ void __launch_bounds__(kFloydWarps * 32) floyd_kernel(FloydArgs a)
 	for (int c = 0; c < NCH; ++c)
 		e7[c] = p5[c] = a1[c] = b1[c] = dout[c] = 0;
 	int known = 0; // boundary entries of the band above known to be published (lane 0 only)
+	int above[8][NCH]; // lane 0: errors from the band above for the current group of 8 texels
+#pragma unroll
+	for (int k = 0; k < 8; ++k)
+#pragma unroll
+		for (int c = 0; c < NCH; ++c)
+			above[k][c] = 0;
+
+	// source texels are fetched kAhead steps before they are needed (a ring of registers, the step loop is unrolled by
+	// kAhead so that ring slots are compile-time): with one warp per band nothing else hides the load latency
+	constexpr int kAhead = 8;
+	auto fetch = [&](int xx) -> uint32_t {
+		if (!live || xx < 0 || xx >= w)
+			return 0u;
+		if (a.srccomps == 4)
+			return __ldg(reinterpret_cast<const uint32_t *>(srow) + xx);
+		const uint8_t *q = srow + (size_t) xx * 3;
+		return (uint32_t) __ldg(q) | ((uint32_t) __ldg(q + 1) << 8) | ((uint32_t) __ldg(q + 2) << 16);
+	};
+	uint32_t ring[kAhead];
+#pragma unroll
+	for (int u = 0; u < kAhead; ++u)
+		ring[u] = fetch(u - 2 * lane);
 
 	const int steps = w + 1 + 2 * 31;
-	for (int s = 0; s < steps; ++s) {
+	for (int s0 = 0; s0 < steps; s0 += kAhead) {
+#pragma unroll
+	for (int u = 0; u < kAhead; ++u) {
+		const int s = s0 + u;
 		const int x = s - 2 * lane;
+		const uint32_t srcw = ring[u];
+		ring[u] = fetch(x + kAhead);
 		// error from the row above for texel x: computed by the lane above in the previous step
 		int din[NCH];
 #pragma unroll
 		for (int c = 0; c < NCH; ++c)
 			din[c] = __shfl_up_sync(0xFFFFFFFFu, dout[c], 1);
-		if (lane == 0) {
-#pragma unroll
-			for (int c = 0; c < NCH; ++c)
-				din[c] = 0;
-			if (x >= 0 && x < w) {
+		if (lane == 0) { // x == s here, so x % kAhead == u: once per unrolled group, fetch the next kAhead boundary entries
+			if (u == 0 && x < w) {
+				const int want = min(x + kAhead, w);
 				if (band > 0) {
-					while (known <= x)
+					while (known < want)
 						known = ld_acquire(a.progress + band - 1);
 #pragma unroll
-					for (int c = 0; c < NCH; ++c)
-						din[c] = __ldcg(bin + (size_t) x * NCH + c);
+					for (int k = 0; k < kAhead; ++k)
+#pragma unroll
+						for (int c = 0; c < NCH; ++c)
+							above[k][c] = x + k < w ? __ldcg(bin + (size_t) (x + k) * NCH + c) : 0;
 				} else if (ALPHA) {
-					din[0] = a.alpha_seed[x]; // the colour pass's leftovers seed alpha row 0
+#pragma unroll
+					for (int k = 0; k < kAhead; ++k)
+						above[k][0] = x + k < w ? a.alpha_seed[x + k] : 0; // the colour pass's leftovers seed alpha row 0
 				}
 			}
+#pragma unroll
+			for (int c = 0; c < NCH; ++c)
+				din[c] = above[u][c];
 		}
 		if (live && x >= 0 && x <= w) {
 			if (x < w) {
-				uint32_t srcw;
-				if (a.srccomps == 4)
-					srcw = __ldg(reinterpret_cast<const uint32_t *>(srow) + x);
-				else {
-					const uint8_t *q = srow + (size_t) x * 3;
-					srcw = (uint32_t) __ldg(q) | ((uint32_t) __ldg(q + 1) << 8) | ((uint32_t) __ldg(q + 2) << 16);
-				}
 				FloydOut o[NCH];
 				int incoming[NCH];
 #pragma unroll
@@ -143,6 +168,7 @@ __global__ void __launch_bounds__(kFloydWarps * 32) floyd_kernel(FloydArgs a)
 					a.alpha_seed[x - 1] = dout[0]; // even height: what the red channel sent below the last row
 			}
 		}
+	}
 	}
 }
 

@@ -150,36 +150,65 @@ dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kind
 // (the "transfer function" of this texel range, exchanged between GPUs when a carry chain is sharded).
 constexpr int kScanThreads = 1024;
 
-__device__ __forceinline__ int scan_lookup(int kind, int table_byte, int state_index)
+constexpr int kScanStage = 8; // tile maps a warp stages in shared memory at a time (8 x 128 B = 1 KB per warp)
+
+// stage tile maps [first, first + kScanStage) of this warp's range: 4 coalesced 128-bit loads per lane, issued together
+__device__ __forceinline__ void scan_stage_load(const ByteMap *__restrict__ tilemaps, size_t first, size_t hi, int lane, uint4 (&regs)[kScanStage / 4])
 {
-	// shift kinds: entry `state_index` of the map whose entry k sits in lane k; bit1: (sum so far + sum) mod 255
-	if (kind == kChanBit1)
-		return (state_index + __shfl_sync(0xFFFFFFFFu, table_byte, 0)) % 255;
-	return __shfl_sync(0xFFFFFFFFu, table_byte, state_index & 31);
+	const uint4 *g = reinterpret_cast<const uint4 *>(tilemaps + first * 4); // 8 uint4 per tile (4 channels x 32 B)
+#pragma unroll
+	for (int q = 0; q < kScanStage / 4; ++q) {
+		const int idx = q * 32 + lane; // 8 uint4 per tile
+		regs[q] = first + (size_t) (idx >> 3) < hi ? __ldg(g + idx) : make_uint4(0, 0, 0, 0);
+	}
 }
 
 __global__ void __launch_bounds__(kScanThreads)
 dither_scan_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKinds kinds, int *carry,
 		int *__restrict__ tile_carry, ByteMap *summary)
 {
-	__shared__ uint8_t s_part[32][4][32]; // map of each warp's tiles
-	__shared__ int s_start[32][4];        // carry entering each warp's tiles
+	__shared__ uint8_t s_part[32][4][32];                 // map of each warp's tiles
+	__shared__ int s_start[32][4];                        // carry entering each warp's tiles
+	__shared__ __align__(16) uint8_t s_stage[32][kScanStage][4][32]; // per warp: staged tile maps
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const size_t per = (ntiles + 31) / 32;
 	const size_t lo = min(ntiles, (size_t) warp * per), hi = min(ntiles, lo + per);
+	bool shift[4], bit1[4];
+	int radius[4];
+#pragma unroll
+	for (int ch = 0; ch < 4; ++ch) {
+		shift[ch] = kinds.k[ch] <= kChanShift4;
+		bit1[ch] = kinds.k[ch] == kChanBit1;
+		radius[ch] = chan_radius(kinds.k[ch]);
+	}
+	uint4 *stage4 = reinterpret_cast<uint4 *>(&s_stage[warp][0][0][0]);
 
-	// phase A: compose this warp's tile maps; acc[ch] = entry `lane` of the composition (bit1: running sum)
+	// phase A: compose this warp's tile maps; acc[ch] = entry `lane` of the composition (bit1: running sum mod 255)
 	int acc[4];
 #pragma unroll
 	for (int ch = 0; ch < 4; ++ch)
-		acc[ch] = kinds.k[ch] == kChanBit1 ? 0 : lane;
-#pragma unroll 4
-	for (size_t i = lo; i < hi; ++i) {
+		acc[ch] = bit1[ch] ? 0 : lane;
+	{
+		uint4 regs[kScanStage / 4];
+		scan_stage_load(tilemaps, lo, hi, lane, regs);
+		for (size_t base = lo; base < hi; base += kScanStage) {
+			__syncwarp();
 #pragma unroll
-		for (int ch = 0; ch < 4; ++ch) {
-			const int b = tilemaps[i * 4 + ch].e[lane];
-			if (kinds.k[ch] <= kChanBit1)
-				acc[ch] = scan_lookup(kinds.k[ch], b, acc[ch]);
+			for (int q = 0; q < kScanStage / 4; ++q)
+				stage4[q * 32 + lane] = regs[q];
+			__syncwarp();
+			if (base + kScanStage < hi)
+				scan_stage_load(tilemaps, base + kScanStage, hi, lane, regs); // in flight while this stage is consumed
+			const int cnt = (int) min((size_t) kScanStage, hi - base);
+			for (int i = 0; i < cnt; ++i) {
+#pragma unroll
+				for (int ch = 0; ch < 4; ++ch) {
+					if (shift[ch])
+						acc[ch] = s_stage[warp][i][ch][acc[ch] & 31]; // out[k] = tile[acc[k]]
+					else if (bit1[ch])
+						acc[ch] = (acc[ch] + s_stage[warp][i][ch][0]) % 255;
+				}
+			}
 		}
 	}
 #pragma unroll
@@ -191,13 +220,12 @@ dither_scan_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKind
 		if (summary) { // fold the 32 partial maps, entry `lane` per lane
 #pragma unroll
 			for (int ch = 0; ch < 4; ++ch) {
-				const int kind = kinds.k[ch];
-				int v = kind == kChanBit1 ? 0 : lane;
-				if (kind <= kChanBit1)
+				int v = bit1[ch] ? 0 : lane;
+				if (shift[ch] || bit1[ch])
 					for (int w = 0; w < 32; ++w)
-						v = kind == kChanBit1 ? (v + s_part[w][ch][0]) % 255 : s_part[w][ch][v & 31];
-				const int ns = chan_states(kind);
-				summary[ch].e[lane] = (uint8_t) ((kind == kChanBit1 ? lane == 0 : lane < ns) ? v : 0);
+						v = bit1[ch] ? (v + s_part[w][ch][0]) % 255 : s_part[w][ch][v & 31];
+				const int ns = chan_states(kinds.k[ch]);
+				summary[ch].e[lane] = (uint8_t) ((bit1[ch] ? lane == 0 : lane < ns) ? v : 0);
 			}
 		} else if (lane < 4) { // phase B: the carry entering each warp's range
 			const int kind = kinds.k[lane];
@@ -218,23 +246,34 @@ dither_scan_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKind
 		return;
 	__syncthreads();
 
-	// phase C: walk this warp's tiles from its carry; the carry is uniform across the warp
+	// phase C: walk this warp's tiles from its carry (all lanes carry the same value; lanes 0..3 store)
 	int c[4];
 #pragma unroll
 	for (int ch = 0; ch < 4; ++ch)
 		c[ch] = s_start[warp][ch];
-#pragma unroll 4
-	for (size_t i = lo; i < hi; ++i) {
-		if (lane < 4)
-			tile_carry[i * 4 + lane] = lane == 0 ? c[0] : (lane == 1 ? c[1] : (lane == 2 ? c[2] : c[3]));
+	{
+		uint4 regs[kScanStage / 4];
+		scan_stage_load(tilemaps, lo, hi, lane, regs);
+		for (size_t base = lo; base < hi; base += kScanStage) {
+			__syncwarp();
 #pragma unroll
-		for (int ch = 0; ch < 4; ++ch) {
-			const int kind = kinds.k[ch];
-			const int b = tilemaps[i * 4 + ch].e[lane];
-			if (kind == kChanBit1)
-				c[ch] = balanced255(c[ch] + __shfl_sync(0xFFFFFFFFu, b, 0));
-			else if (kind <= kChanShift4)
-				c[ch] = __shfl_sync(0xFFFFFFFFu, b, c[ch] + chan_radius(kind)) - chan_radius(kind);
+			for (int q = 0; q < kScanStage / 4; ++q)
+				stage4[q * 32 + lane] = regs[q];
+			__syncwarp();
+			if (base + kScanStage < hi)
+				scan_stage_load(tilemaps, base + kScanStage, hi, lane, regs);
+			const int cnt = (int) min((size_t) kScanStage, hi - base);
+			for (int i = 0; i < cnt; ++i) {
+				if (lane < 4)
+					tile_carry[(base + i) * 4 + lane] = lane == 0 ? c[0] : (lane == 1 ? c[1] : (lane == 2 ? c[2] : c[3]));
+#pragma unroll
+				for (int ch = 0; ch < 4; ++ch) {
+					if (shift[ch])
+						c[ch] = (int) s_stage[warp][i][ch][c[ch] + radius[ch]] - radius[ch];
+					else if (bit1[ch])
+						c[ch] = balanced255(c[ch] + s_stage[warp][i][ch][0]);
+				}
+			}
 		}
 	}
 }
