@@ -343,8 +343,17 @@ def main():
         int32 = {"kernel": "pair_search", "achieved": a, "peak": int32_peak, "unit": "Gop/s (int32 min+add)",
                  "frac": a / int32_peak if int32_peak else None,
                  "ops_per_block": int_ops_block, "peak_source": "measured in this run (s2tc_b200_int32_peak)"}
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            rec = json.load(f).get(args.workload, {}).get(dom)
+        if rec and not args.size:
+            traffic = {"dram_bytes_per_launch": rec["dram_bytes"], "blocks_per_launch": rec["blocks_per_launch"],
+                       "bytes_per_block": rec["dram_bytes"] / rec["blocks_per_launch"], "source": rec["source"]}
+    except OSError:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_block": alg_bytes, "ms_per_launch": dom_ms_launch,
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in fam.items() if v[1]},
                 "int32": int32}
