@@ -348,8 +348,9 @@ def main():
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             rec = json.load(f).get(args.workload, {}).get(dom)
         if rec and not args.size:
-            traffic = {"dram_bytes_per_launch": rec["dram_bytes"], "blocks_per_launch": rec["blocks_per_launch"],
-                       "bytes_per_block": rec["dram_bytes"] / rec["blocks_per_launch"], "source": rec["source"]}
+            per_block = rec["dram_bytes"] / rec["blocks_per_launch"]
+            traffic = {"dram_bytes_per_launch": per_block * per_launch_blocks, "bytes_per_block": per_block,
+                       "captured_blocks_per_launch": rec["blocks_per_launch"], "source": rec["source"]}
     except OSError:
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",

@@ -238,8 +238,9 @@ int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int
 	}
 
 	// MODE_NORMAL goes slab by slab to bound the candidate/endpoint workspaces
-	const bool fast = is_fast_mode(s.cd, s.nrandom);
-	long long rows_per_slab = fast ? (row1 - row0) : (kSlabBlocks / bw > 0 ? kSlabBlocks / bw : 1);
+	// only the random-candidate path has per-block workspaces to bound; the fused kernels take the range in one launch
+	const bool one_launch = s.nrandom <= 0;
+	long long rows_per_slab = one_launch ? (row1 - row0) : (kSlabBlocks / bw > 0 ? kSlabBlocks / bw : 1);
 	const int bs = block_bytes(s.dxt);
 	for (long long r = row0; r < row1; r += rows_per_slab) {
 		const int r1 = (int) (r + rows_per_slab < row1 ? r + rows_per_slab : row1);

@@ -339,6 +339,70 @@ dither_apply_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits
 	}
 }
 
+// Images of at most one tile (16384 texels: every mip level from 128x128 down) do all three phases in ONE CTA:
+// chunk maps -> walk from the given carry -> replay.  The three-kernel path costs ~70 us of fixed latency per image,
+// which dominated mip chains (12 levels per texture).
+__global__ void __launch_bounds__(kTileThreads)
+dither_small_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits, ChanKinds kinds, int npixels,
+		const DitherLut *__restrict__ lut, int *carry /* 4 ints in/out */, uint32_t *__restrict__ out)
+{
+	__shared__ __align__(16) uint32_t s_lut3[256][4];
+	__shared__ uint32_t s_lut2[256];
+	__shared__ ByteMap s_maps[kTileThreads * 4];
+	__shared__ int s_carry[kTileThreads * 4];
+	const int t = threadIdx.x;
+	for (int i = t; i < 256 * 4; i += kTileThreads)
+		(&s_lut3[0][0])[i] = (&lut->lut3[0][0])[i];
+	for (int i = t; i < 256; i += kTileThreads)
+		s_lut2[i] = lut->lut2[i];
+	__syncthreads();
+	const int first = t * kChunk;
+	const int count = first >= npixels ? 0 : min(kChunk, npixels - first);
+	auto texel = [&](int i) -> uint32_t {
+		if (srccomps == 4)
+			return __ldg(reinterpret_cast<const uint32_t *>(src) + first + i);
+		const uint8_t *q = src + (size_t) (first + i) * 3;
+		return (uint32_t) __ldg(q) | ((uint32_t) __ldg(q + 1) << 8) | ((uint32_t) __ldg(q + 2) << 16);
+	};
+	{
+		RgbTables tab;
+		rgb_tables_init(tab);
+		uint32_t asum = 0;
+		for (int i = count; i > 0; --i) {
+			const uint32_t w = texel(i - 1);
+			rgb_tables_prepend(tab, w, s_lut3, s_lut2);
+			asum += w >> 24;
+		}
+		ByteMap m[4];
+		rgb_tables_store(tab, m[0], m[1], m[2]);
+		if (kinds.k[3] == kChanShift4)
+			alpha_map_of_run(m[3], kChanShift4, src + (size_t) first * 4 + 3, 4, count);
+		else {
+#pragma unroll
+			for (int k = 0; k < 32; ++k)
+				m[3].e[k] = 0;
+			m[3].e[0] = (uint8_t) (asum % 255u);
+		}
+#pragma unroll
+		for (int ch = 0; ch < 4; ++ch)
+			s_maps[t * 4 + ch] = m[ch];
+	}
+	__syncthreads();
+	if (t < 4) {
+		int c = carry[t];
+		const int kind = kinds.k[t];
+		for (int i = 0; i < kTileThreads; ++i) {
+			s_carry[i * 4 + t] = c;
+			c = bmap_apply(s_maps[i * 4 + t], kind, c);
+		}
+		carry[t] = c;
+	}
+	__syncthreads();
+	int cc[4] = {s_carry[t * 4 + 0], s_carry[t * 4 + 1], s_carry[t * 4 + 2], s_carry[t * 4 + 3]};
+	for (int i = 0; i < count; ++i)
+		out[first + i] = replay_texel(cc, texel(i), kinds.k[3], srccomps == 4, alphabits);
+}
+
 static size_t dither_tiles(size_t npixels) { return (npixels + kTilePixels - 1) / kTilePixels; }
 
 // workspace: chunk maps [tiles*128][4] | tile maps [tiles][4] | tile carries [tiles][4]
@@ -384,6 +448,11 @@ static cudaError_t run_dither(int phases, const void *d_src, int srccomps, int a
 	const DitherLut *lut = device_dither_lut(&e);
 	if (!lut)
 		return e;
+	if (phases == 7 && npixels <= (size_t) kTilePixels) { // one tile, full pass: the fused single-CTA kernel
+		dither_small_kernel<<<1, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, alphabits, kinds, (int) npixels, lut,
+				d_carry, (uint32_t *) d_reduced);
+		return cudaGetLastError();
+	}
 	if (phases & 1)
 		dither_maps_kernel<<<(unsigned) tiles, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, kinds, npixels, lut,
 				chunkmaps, tilemaps);
