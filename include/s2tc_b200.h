@@ -118,6 +118,11 @@ int s2tc_b200_encode_block_host(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s,
 int s2tc_b200_transcode_host(s2tc_b200_ctx *ctx, int dxt, uint8_t *blocks, size_t nblocks);
 int s2tc_b200_transcode_device(s2tc_b200_ctx *ctx, int dxt, void *d_blocks, size_t nblocks, void *stream);
 
+/* ---- S2TC decode of whole images (SURVEY "next" N4): what calling fetch_2d_texel_rgba_dxt1/3/5
+ * (ref s2tc_libtxc_dxtn.cpp:57-140) for every texel gives; blocks tightly packed, RGBA8 out ------------------- */
+int s2tc_b200_decode_device(s2tc_b200_ctx *ctx, int dxt, const void *d_blocks, int width, int height, void *d_rgba, void *stream);
+int s2tc_b200_decode_host(s2tc_b200_ctx *ctx, int dxt, const uint8_t *blocks, int width, int height, uint8_t *rgba);
+
 /* Settings as tx_compress_dxtn would read them from the S2TC_* environment right now (warnings on stderr for
  * bad values, as in ref s2tc_libtxc_dxtn.cpp:160-216), for callers of the explicit-settings functions. */
 void s2tc_b200_settings_from_env(int dxt, s2tc_b200_settings *out);

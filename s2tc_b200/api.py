@@ -138,6 +138,8 @@ def lib():
     L.s2tc_b200_mip_reduce_device.argtypes = [vp, vp, i32, i32, vp, vp]
     L.s2tc_b200_compress_mipchain_device.argtypes = [vp, sp, i32, i32, vp, vp, vp, C.POINTER(u64), vp]
     L.s2tc_b200_compress_mipchain_host.argtypes = [vp, sp, i32, i32, vp, vp, C.POINTER(u64)]
+    L.s2tc_b200_decode_device.argtypes = [vp, i32, vp, i32, i32, vp, vp]
+    L.s2tc_b200_decode_host.argtypes = [vp, i32, vp, i32, i32, vp]
     L.s2tc_b200_rgb565_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32]
     L.s2tc_b200_encode_block_host.argtypes = [vp, sp, vp, vp, i32, i32, i32, C.POINTER(u64)]
     L.s2tc_b200_transcode_host.argtypes = [vp, i32, vp, C.c_size_t]
@@ -256,6 +258,13 @@ class Encoder:
         cur = C.c_uint64(cursor)
         s = settings.c()
         _check(lib().s2tc_b200_encode_block_host(self._ctx, C.byref(s), _addr(out), _addr(px), iw, w, h, C.byref(cur)))
+        return out
+
+    def decode(self, blocks, dxt, width, height):
+        """S2TC blocks -> (H, W, 4) RGBA8, the result of the reference's per-texel fetchers applied to every texel."""
+        b = np.ascontiguousarray(blocks, np.uint8).reshape(-1)
+        out = np.zeros((height, width, 4), np.uint8)
+        _check(lib().s2tc_b200_decode_host(self._ctx, dxt, _addr(b), width, height, _addr(out)))
         return out
 
     def transcode(self, blocks, dxt):

@@ -708,6 +708,44 @@ int s2tc_b200_transcode_host(s2tc_b200_ctx *c, int dxt, uint8_t *blocks, size_t 
 	return 0;
 }
 
+int s2tc_b200_decode_device(s2tc_b200_ctx *c, int dxt, const void *d_blocks, int width, int height, void *d_rgba, void *stream)
+{
+	if (!c || !d_blocks || !d_rgba)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	if ((dxt != kDxt1 && dxt != kDxt3 && dxt != kDxt5) || width <= 0 || height <= 0)
+		return fail(S2TC_B200_EINVAL, "bad argument");
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	FamScope f(c, st, kFamTranscode, 1);
+	CU(launch_decode(dxt, d_blocks, width, height, d_rgba, st));
+	return 0;
+}
+
+int s2tc_b200_decode_host(s2tc_b200_ctx *c, int dxt, const uint8_t *blocks, int width, int height, uint8_t *rgba)
+{
+	if (!c || !blocks || !rgba)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	if ((dxt != kDxt1 && dxt != kDxt3 && dxt != kDxt5) || width <= 0 || height <= 0)
+		return fail(S2TC_B200_EINVAL, "bad argument");
+	const size_t nb = (size_t) ((width + 3) / 4) * ((height + 3) / 4) * block_bytes(dxt), np = (size_t) width * height * 4;
+	void *d_b, *d_p;
+	{
+		std::lock_guard<std::mutex> lock(c->mu);
+		CU(cudaSetDevice(c->device));
+		CU(c->out.reserve(nb));
+		CU(c->src.reserve(np));
+		d_b = c->out.p; d_p = c->src.p;
+		CU(cudaMemcpyAsync(d_b, blocks, nb, cudaMemcpyHostToDevice, c->stream));
+	}
+	if (int rc = s2tc_b200_decode_device(c, dxt, d_b, width, height, d_p, nullptr))
+		return rc;
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaMemcpyAsync(rgba, d_p, np, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
 static std::mutex g_cursor_mu;
 static uint64_t g_cursor = 0;
 uint64_t s2tc_b200_rand_cursor_get(void)

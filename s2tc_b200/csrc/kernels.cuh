@@ -151,6 +151,9 @@ cudaError_t launch_prepass_floyd(const void *d_src, int srccomps, int alphabits,
 // one mip step of an RGBA8 image (w x h -> max(w/2,1) x max(h/2,1)); d_out must not alias d_in
 cudaError_t launch_mip_reduce(const void *d_in, int w, int h, void *d_out, cudaStream_t stream);
 
+// S2TC decode of a whole image to RGBA8 (tightly packed blocks in, width*height*4 bytes out)
+cudaError_t launch_decode(int dxt, const void *d_blocks, int width, int height, void *d_rgba, cudaStream_t stream);
+
 // S3TC -> S2TC transcode, in place.
 cudaError_t launch_transcode(int dxt, void *d_blocks, size_t nblocks, cudaStream_t stream);
 

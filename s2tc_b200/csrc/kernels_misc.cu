@@ -704,6 +704,68 @@ cudaError_t launch_mip_reduce(const void *d_in, int w, int h, void *d_out, cudaS
 }
 
 // =====================================================================================================
+// S2TC decode (reference fetch_2d_texel_rgba_dxt1/3/5, s2tc_libtxc_dxtn.cpp:57-140; SURVEY "next" N4): whole images
+// instead of one texel per call.  One thread per texel; codes that S3TC would interpolate show as a checkerboard
+// of the two endpoints ((x ^ y) & 1), DXT1 code 3 with c1 >= c0 is transparent black.
+// =====================================================================================================
+__global__ void decode_kernel(int dxt, const uint8_t *__restrict__ blocks, int width, int height, uint32_t *__restrict__ out)
+{
+	const size_t n = (size_t) width * height, stride = (size_t) gridDim.x * blockDim.x;
+	const int bw = (width + 3) >> 2, bs = dxt == kDxt1 ? 8 : 16;
+	for (size_t p = (size_t) blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+		const int y = (int) (p / width), x = (int) (p - (size_t) y * width);
+		const uint8_t *blk = blocks + ((size_t) (y >> 2) * bw + (x >> 2)) * bs;
+		const uint2 cw = __ldg(reinterpret_cast<const uint2 *>(blk + (dxt == kDxt1 ? 0 : 8)));
+		const uint32_t c0 = cw.x & 0xFFFFu, c1 = cw.x >> 16;
+		const uint32_t code = (cw.y >> (2 * ((y & 3) * 4 + (x & 3)))) & 3u;
+		uint32_t c = c0, alpha = 255;
+		if (code == 1)
+			c = c1;
+		else if (code == 3 && dxt == kDxt1 && c1 >= c0) {
+			c = 0;
+			alpha = 0;
+		} else if (code >= 2 && ((x ^ y) & 1))
+			c = c1;
+		const uint32_t r5 = (c >> 11) & 31u, g6 = (c >> 5) & 63u, b5 = c & 31u;
+		const uint32_t r = (r5 << 3) | (r5 >> 2), g = (g6 << 2) | (g6 >> 4), b = (b5 << 3) | (b5 >> 2);
+		if (dxt == kDxt3) {
+			const uint2 aw = __ldg(reinterpret_cast<const uint2 *>(blk));
+			const int i = (y & 3) * 4 + (x & 3);
+			const uint32_t a4 = ((i < 8 ? aw.x >> (4 * i) : aw.y >> (4 * (i - 8)))) & 15u;
+			alpha = a4 | (a4 << 4);
+		} else if (dxt == kDxt5) {
+			const uint2 aw = __ldg(reinterpret_cast<const uint2 *>(blk));
+			const uint32_t a0 = aw.x & 0xFFu, a1 = (aw.x >> 8) & 0xFFu;
+			const uint64_t bits = (((uint64_t) aw.y << 32) | aw.x) >> 16;
+			const uint32_t ac = (uint32_t) (bits >> (3 * ((y & 3) * 4 + (x & 3)))) & 7u;
+			alpha = a0;
+			if (ac == 1)
+				alpha = a1;
+			else if (ac == 6 && a1 >= a0)
+				alpha = 0;
+			else if (ac == 7 && a1 >= a0)
+				alpha = 255;
+			else if (ac >= 2 && ((x ^ y) & 1))
+				alpha = a1;
+		}
+		out[p] = r | (g << 8) | (b << 16) | (alpha << 24);
+	}
+}
+
+cudaError_t launch_decode(int dxt, const void *d_blocks, int width, int height, void *d_rgba, cudaStream_t stream)
+{
+	const size_t n = (size_t) width * height;
+	if (!n)
+		return cudaSuccess;
+	const int threads = 256;
+	size_t blocks = (n + threads - 1) / threads;
+	if (blocks > 148 * 32)
+		blocks = 148 * 32;
+	decode_kernel<<<(unsigned) blocks, threads, 0, stream>>>(dxt, (const uint8_t *) d_blocks, width, height, (uint32_t *) d_rgba);
+	return cudaGetLastError();
+}
+
+// =====================================================================================================
 // Measurement aid: sustained INT32 min+add issue rate, the denominator for the search kernels' roofline
 // (search modes are bound by the integer pipes, not by HBM).  8 independent chains per
 // thread of exactly the two operations the pair scan is made of (IMNMX + IADD).

@@ -152,6 +152,30 @@ def test_mip_chain_on_device(encoder):
             assert cur == cursor
 
 
+def test_decode_whole_images(encoder):
+    """GPU decoder against the oracle's restatement of fetch_2d_texel_* on encoder output and on arbitrary block bytes
+    (all index codes), plus a sanity bound on the encode -> decode error of an opaque gradient."""
+    import ctypes
+    u8p = ctypes.POINTER(ctypes.c_ubyte)
+    rng = np.random.default_rng(5)
+    for dxt in (O.DXT1, O.DXT3, O.DXT5):
+        w, h = 37, 22
+        blocks = rng.integers(0, 256, size=((w + 3) // 4) * ((h + 3) // 4) * O.block_bytes(dxt), dtype=np.uint8)
+        got = encoder.decode(blocks, dxt, w, h)
+        want = np.zeros((h, w, 4), np.uint8)
+        t = np.zeros(4, np.uint8)
+        for y in range(h):
+            for x in range(w):
+                O.lib().orc_fetch_texel(dxt, 0, w, blocks.ctypes.data_as(u8p), x, y, t.ctypes.data_as(u8p))
+                want[y, x] = t
+        assert np.array_equal(got, want), dxt
+    img = synth.synth_rgba(128, 128, seed=3)
+    img[..., 3] = 255
+    dec = encoder.decode(encoder.compress(img, Settings(O.DXT5, O.WAVG, 0, O.LOOP, O.DITHER_NONE)), O.DXT5, 128, 128)
+    err = np.abs(dec[..., :3].astype(int) - img[..., :3].astype(int)).mean()
+    assert err < 12 and (dec[..., 3] == 255).all(), err
+
+
 def test_transcode(encoder):
     for dxt in (O.DXT1, O.DXT3, O.DXT5):
         blocks = synth.synth_s3tc_blocks(4096, dxt)
