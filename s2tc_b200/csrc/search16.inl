@@ -183,18 +183,34 @@ __global__ void __launch_bounds__(128, S2TC_ENCODE16_MINBLOCKS) encode16_kernel(
 	int a0 = 0, a1 = 0;
 	if (DXT == kDxt5) {
 		int a[16];
+		bool flat = true; // every gathered alpha equal
 #pragma unroll
 		for (int k = 0; k < 16; ++k) {
 			a[k] = (int) (cl[k] >> 24); // re-read: c[] is dead by now, which keeps the scan's live set at the matrix itself
-			fix[k] = k < n ? min(a[k] * a[k], (255 - a[k]) * (255 - a[k])) : 0;
+			flat = flat && (k >= n || a[k] == a[0]);
 		}
-		fill120(D, n, [&](auto i, auto k) {
-			const int d = a[decltype(i)::value] - a[decltype(k)::value];
-			return d * d;
-		}, std::make_integer_sequence<int, 120>{});
-		const uint32_t aij = scan120<false, true>(D, fix, n, std::make_integer_sequence<int, 120>{});
-		a0 = (int) (cl[aij >> 4] >> 24);
-		a1 = (int) (cl[aij & 15u] >> 24);
+		// Exact shortcut: with a single alpha value every distance is 0, every pair sums to 0, and the reference keeps
+		// its first pair (0,1) (ref :467-477).  Measured on config 2 (75 % flat blocks, 32 % flat warps) it made the kernel
+		// SLOWER (4.21 ms vs 3.11 ms without it, same box, A/B builds), so it is off unless S2TC_ENCODE16_FLAT_ALPHA is
+		// defined; the split into two branches is kept because it removed the DXT5 register spills (3.57 -> 3.11 ms).
+#ifndef S2TC_ENCODE16_FLAT_ALPHA
+		flat = false;
+#endif
+		if (__all_sync(__activemask(), flat)) {
+			a0 = a[0];
+			a1 = a[1];
+		} else {
+#pragma unroll
+			for (int k = 0; k < 16; ++k)
+				fix[k] = k < n ? min(a[k] * a[k], (255 - a[k]) * (255 - a[k])) : 0;
+			fill120(D, n, [&](auto i, auto k) {
+				const int d = a[decltype(i)::value] - a[decltype(k)::value];
+				return d * d;
+			}, std::make_integer_sequence<int, 120>{});
+			const uint32_t aij = scan120<false, true>(D, fix, n, std::make_integer_sequence<int, 120>{});
+			a0 = (int) (cl[aij >> 4] >> 24);
+			a1 = (int) (cl[aij & 15u] >> 24);
+		}
 	}
 
 	// ---- refinement and packing (ref :1010-1107) ---------------------------------------------------------
