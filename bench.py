@@ -234,10 +234,18 @@ def main():
             carry = enc.carry_apply(m, 4, abits, carry)
         return carry
 
+    maps_mine = torch.zeros(16, dtype=torch.int64, device="cuda")
+    maps_all = torch.zeros(16 * world, dtype=torch.int64, device="cuda")
+    carry_dev = torch.zeros(4, dtype=torch.int32, device="cuda")
+
     def step_device():
-        carry = incoming_carry()
-        enc.encode_rows_device(d_src, width, total_h, 4, row0, row1, d_dst, st, cursor0=0, carry=carry,
-                               stream=stream.cuda_stream)
+        if world == 1:
+            enc.encode_rows_device(d_src, width, total_h, 4, row0, row1, d_dst, st, cursor0=0, carry=None,
+                                   stream=stream.cuda_stream)
+        else:   # summary -> all-gather (128 B per rank, NCCL) -> fold -> encode, all on the device, no host sync
+            enc.sharded_encode_async(d_src, width, total_h, 4, row0, row1, d_dst, st, maps_mine,
+                                     lambda: dist.all_gather_into_tensor(maps_all, maps_mine), maps_all, rank, carry_dev,
+                                     cursor0=0, stream=stream.cuda_stream)
 
     def step_e2e():
         if world == 1:

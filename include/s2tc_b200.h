@@ -92,6 +92,18 @@ int s2tc_b200_dither_summary_device(s2tc_b200_ctx *ctx, int srccomps, int alphab
 		const void *d_src_rows, int row0, int row1, uint64_t maps[16], void *stream);
 int s2tc_b200_carry_apply(const uint64_t map[4], int channel, int srccomps, int alphabits, int carry_in);
 
+/* Fully asynchronous forms of the sharding primitives (no host synchronisation; everything stays on `stream`):
+ *   _dither_summary_async : the 128-byte summary of this shard's texels is written to device memory (d_maps)
+ *   _fold_carry_async     : d_all_maps = the shards' summaries in rank order (e.g. the result of an all-gather);
+ *                           writes the carry entering shard `rank` to d_carry (4 ints, device)
+ *   _encode_rows_async    : s2tc_b200_encode_rows_device with the carry read from / updated in device memory */
+int s2tc_b200_dither_summary_async(s2tc_b200_ctx *ctx, int srccomps, int alphabits, int width, int height,
+		const void *d_src_rows, int row0, int row1, void *d_maps, void *stream);
+int s2tc_b200_fold_carry_async(s2tc_b200_ctx *ctx, const void *d_all_maps, int rank, int srccomps, int alphabits, int *d_carry,
+		void *stream);
+int s2tc_b200_encode_rows_async(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int srccomps, int width, int height,
+		const void *d_src_rows, int row0, int row1, void *d_dst, uint64_t rand_cursor0, int *d_carry, void *stream);
+
 /* ---- whole mip chain of an RGBA8 image on the device (SURVEY "next" N2) -----------------------------------
  * What the reference tool does per file after the DDS header (s2tc_compress.c:722-733): encode the level with
  * one tx_compress_dxtn call, halve it with Image_MipReduce32 (:427-493), repeat down to 1x1.  Every level is its own

@@ -132,6 +132,9 @@ def lib():
     L.s2tc_b200_compress_host.argtypes = [vp, sp, i32, i32, i32, vp, vp, i32, C.POINTER(u64)]
     L.s2tc_b200_encode_rows_device.argtypes = [vp, sp, i32, i32, i32, vp, i32, i32, vp, u64, C.POINTER(i32), vp]
     L.s2tc_b200_dither_summary_device.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, C.POINTER(u64), vp]
+    L.s2tc_b200_dither_summary_async.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp]
+    L.s2tc_b200_fold_carry_async.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+    L.s2tc_b200_encode_rows_async.argtypes = [vp, sp, i32, i32, i32, vp, i32, i32, vp, u64, vp, vp]
     L.s2tc_b200_carry_apply.argtypes = [C.POINTER(u64), i32, i32, i32, i32]
     L.s2tc_b200_mipchain_bytes.argtypes = [i32, i32, i32]
     L.s2tc_b200_mipchain_bytes.restype = C.c_size_t
@@ -286,6 +289,21 @@ class Encoder:
                                                   _addr(dst), cursor0, cptr, stream))
         if carry is not None:
             carry[:] = list(arr)
+
+    def sharded_encode_async(self, src_rows, width, height, comps, row0, row1, dst, settings, maps_mine, all_gather, maps_all,
+                             rank, carry_dev, cursor0=0, stream=None):
+        """One shard of a DITHER_SIMPLE image without host synchronisation: summary -> all_gather() (a callable that
+        gathers `maps_mine` (16 int64, device) of every rank into `maps_all` on the same stream) -> fold -> encode."""
+        s = settings.c()
+        abits = {DXT1: 1, DXT3: 4, DXT5: 8}[settings.dxt]
+        if settings.dither == DITHER_SIMPLE:
+            _check(lib().s2tc_b200_dither_summary_async(self._ctx, comps, abits, width, height, _addr(src_rows), row0, row1,
+                                                        _addr(maps_mine), stream))
+            all_gather()
+            _check(lib().s2tc_b200_fold_carry_async(self._ctx, _addr(maps_all), rank, comps, abits, _addr(carry_dev), stream))
+        _check(lib().s2tc_b200_encode_rows_async(self._ctx, C.byref(s), comps, width, height, _addr(src_rows), row0, row1,
+                                                 _addr(dst), cursor0, _addr(carry_dev) if settings.dither == DITHER_SIMPLE else None,
+                                                 stream))
 
     def dither_summary_device(self, src_rows, width, height, comps, alphabits, row0, row1, stream=None):
         maps = (C.c_uint64 * 16)()

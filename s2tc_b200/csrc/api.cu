@@ -372,6 +372,62 @@ int s2tc_b200_encode_rows_device(s2tc_b200_ctx *c, const s2tc_b200_settings *sin
 	return 0;
 }
 
+// Fully asynchronous variant for sharded encodes: the summary stays on the device (d_maps, 128 bytes) so that it can
+// be all-gathered and folded there without a host round trip.
+int s2tc_b200_dither_summary_async(s2tc_b200_ctx *c, int srccomps, int alphabits, int width, int height,
+		const void *d_src_rows, int row0, int row1, void *d_maps, void *stream)
+{
+	if (!c || !d_src_rows || !d_maps)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	const int bh = (height + 3) / 4;
+	if (width <= 0 || height <= 0 || row0 < 0 || row1 > bh || row0 >= row1)
+		return fail(S2TC_B200_EINVAL, "bad geometry");
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	const int comps = srccomps == 3 ? 3 : 4;
+	const int y0 = row0 * 4, y1 = row1 * 4 < height ? row1 * 4 : height;
+	const size_t npix = (size_t) width * (y1 - y0);
+	CU(c->dither_ws.reserve(dither_workspace_bytes(npix)));
+	FamScope f(c, st, kFamPrepass, 2);
+	CU(launch_dither_summary(d_src_rows, comps, alphabits, npix, (ByteMap *) d_maps, c->dither_ws.p, st));
+	c->maps_src = d_src_rows;
+	c->maps_npix = npix;
+	c->maps_comps = comps;
+	c->maps_abits = alphabits;
+	return 0;
+}
+
+// Folds the summaries of shards 0 .. rank-1 (d_all_maps: `rank` or more consecutive 128-byte summaries on the device)
+// into the carry entering shard `rank`; d_carry: 4 ints on the device.  Asynchronous.
+int s2tc_b200_fold_carry_async(s2tc_b200_ctx *c, const void *d_all_maps, int rank, int srccomps, int alphabits, int *d_carry,
+		void *stream)
+{
+	if (!c || !d_all_maps || !d_carry || rank < 0)
+		return fail(S2TC_B200_EINVAL, "bad argument");
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	FamScope f(c, st, kFamPrepass, 1);
+	CU(launch_fold_carry((const ByteMap *) d_all_maps, rank, srccomps == 3 ? 3 : 4, alphabits, d_carry, st));
+	return 0;
+}
+
+// encode_rows with the DITHER_SIMPLE carry on the device (in/out), no host synchronisation
+int s2tc_b200_encode_rows_async(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int srccomps, int width, int height,
+		const void *d_src_rows, int row0, int row1, void *d_dst, uint64_t rand_cursor0, int *d_carry, void *stream)
+{
+	if (!c || !d_src_rows || !d_dst)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	s2tc_b200_settings s;
+	if (int rc = settings_normalise(sin, s))
+		return rc;
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	return encode_rows(c, s, srccomps, width, height, d_src_rows, row0, row1, d_dst, rand_cursor0, d_carry, st);
+}
+
 int s2tc_b200_dither_summary_device(s2tc_b200_ctx *c, int srccomps, int alphabits, int width, int height,
 		const void *d_src_rows, int row0, int row1, uint64_t maps[16], void *stream)
 {

@@ -143,6 +143,8 @@ cudaError_t launch_prepass_simple(const void *d_src, int srccomps, int alphabits
 cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits, size_t npixels,
 		ByteMap *d_summary, void *d_workspace, cudaStream_t stream);
 
+cudaError_t launch_fold_carry(const ByteMap *d_maps, int rank, int srccomps, int alphabits, int *d_carry, cudaStream_t stream);
+
 // DITHER_FLOYDSTEINBERG over a whole width x height image (a 2-D recurrence: it cannot start in the middle)
 size_t floyd_workspace_bytes(int width, int height);
 cudaError_t launch_prepass_floyd(const void *d_src, int srccomps, int alphabits, int width, int height, void *d_reduced,

@@ -464,6 +464,24 @@ static cudaError_t run_dither(int phases, const void *d_src, int srccomps, int a
 	return cudaGetLastError();
 }
 
+// carry entering shard `rank` = summaries of shards 0 .. rank-1 applied in order to a zero carry (one thread per channel)
+__global__ void fold_carry_kernel(const ByteMap *__restrict__ maps, int rank, ChanKinds kinds, int *carry)
+{
+	const int ch = threadIdx.x;
+	if (ch >= 4)
+		return;
+	int c = 0;
+	for (int r = 0; r < rank; ++r)
+		c = bmap_apply(maps[r * 4 + ch], kinds.k[ch], c);
+	carry[ch] = c;
+}
+
+cudaError_t launch_fold_carry(const ByteMap *d_maps, int rank, int srccomps, int alphabits, int *d_carry, cudaStream_t stream)
+{
+	fold_carry_kernel<<<1, 32, 0, stream>>>(d_maps, rank, chan_kinds(srccomps, alphabits), d_carry);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_prepass_simple(const void *d_src, int srccomps, int alphabits, size_t npixels, void *d_reduced,
 		int *d_carry, void *d_workspace, bool maps_ready, cudaStream_t stream)
 {

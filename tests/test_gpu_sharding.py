@@ -43,3 +43,38 @@ def test_sharded_rows_equal_whole_image(encoder, dxt, cd, nr, rf, dither):
         stream.synchronize()
     got = np.concatenate([o.cpu().numpy() for _, o in sorted(outs, key=lambda x: x[0])])
     assert np.array_equal(got, want)
+
+
+def test_sharded_rows_async_device_side_carry(encoder):
+    """The no-host-sync protocol bench.py uses at N > 1: summaries written to device memory, gathered (here: placed
+    side by side by hand), folded on the device, and the carry handed to the encode as a device pointer."""
+    import ctypes as C
+    import s2tc_b200
+    from s2tc_b200.api import _addr, _check, lib
+    width, height, world = 200, 150, 4
+    img = synth.synth_noise(width, height, seed=43)
+    dxt, cd, nr, rf = O.DXT3, O.WAVG, 5, O.LOOP
+    st = Settings(dxt, cd, nr, rf, O.DITHER_SIMPLE)
+    s = st.c()
+    bw, bh = (width + 3) // 4, (height + 3) // 4
+    want = O.orc_compress(img, dxt, cd, nr, rf, O.DITHER_SIMPLE, cursor=3)
+    d_img = torch.from_numpy(img).cuda()
+    ranges = [shard_block_rows(bh, world, r) for r in range(world)]
+    shards = [d_img[4 * a:min(4 * b, height)].contiguous() for a, b in ranges]
+    maps_all = torch.zeros(16 * world, dtype=torch.int64, device="cuda")
+    carry = torch.zeros(4, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.Stream()
+    outs = []
+    with torch.cuda.stream(stream):
+        for r, (a, b) in enumerate(ranges):   # "all-gather": every shard's summary lands in its slot
+            _check(lib().s2tc_b200_dither_summary_async(encoder._ctx, 4, 4, width, height, _addr(shards[r]), a, b,
+                                                        maps_all[16 * r:].data_ptr(), stream.cuda_stream))
+        for r, (a, b) in enumerate(ranges):
+            _check(lib().s2tc_b200_fold_carry_async(encoder._ctx, _addr(maps_all), r, 4, 4, _addr(carry), stream.cuda_stream))
+            d_out = torch.zeros((b - a) * bw * 16, dtype=torch.uint8, device="cuda")
+            _check(lib().s2tc_b200_encode_rows_async(encoder._ctx, C.byref(s), 4, width, height, _addr(shards[r]), a, b,
+                                                     _addr(d_out), 3, _addr(carry), stream.cuda_stream))
+            outs.append(d_out)
+        stream.synchronize()
+    got = np.concatenate([o.cpu().numpy() for o in outs])
+    assert np.array_equal(got, want)
