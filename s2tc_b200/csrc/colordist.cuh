@@ -74,27 +74,44 @@ template <int CD> struct LinearMetric {
 	static S2TC_HD Feat feat(uint32_t p) { return Feat{px_r(p), px_g(p), px_b(p)}; }
 };
 
-template <> struct Metric<kAVG> : LinearMetric<kAVG> { // ref :217-223, <= 11657
-	static S2TC_HD int dist(const FeatRGB &a, const FeatRGB &b)
+// AVG / W0AVG / WAVG are sums of squares of integer-weighted channel differences (weights 2,1,2 / 1,1,1 / 2,2,1 on
+// dr, dg, db).  The feature is the colour with its channels pre-scaled, one per byte (all < 128); a distance is then one
+// borrow-free per-byte subtraction and one 4-way dot product of the difference with itself (IDP.4A): 3 instructions
+// instead of ~9, in the fast kernel, the refinement passes and the distance-matrix fills alike.
+struct FeatBytes { uint32_t v; };
+
+S2TC_HD int dot4_self(uint32_t d) // sum of squares of the four signed bytes of d
+{
+#if defined(__CUDA_ARCH__)
+	return __dp4a((int) d, (int) d, 0);
+#else
+	int s = 0;
+	for (int i = 0; i < 4; ++i) {
+		const int b = (int) (signed char) (d >> (8 * i));
+		s += b * b;
+	}
+	return s;
+#endif
+}
+
+template <uint32_t DOUBLED /* mask of the channels weighted 2 */> struct SquareMetric {
+	typedef FeatBytes Feat;
+	static constexpr bool kMayBeNegative = false;
+	static S2TC_HD Feat feat(uint32_t p)
 	{
-		int dr = a.r - b.r, dg = a.g - b.g, db = a.b - b.b;
-		return ((dr * dr) << 2) + dg * dg + ((db * db) << 2);
+		const uint32_t rgb = p & 0x00FFFFFFu;
+		return Feat{rgb + (rgb & DOUBLED)}; // r <= 31, g <= 63, b <= 31: doubling never carries into the next byte
+	}
+	static S2TC_HD int dist(const FeatBytes &a, const FeatBytes &b)
+	{
+		// bytes of a.v and b.v are < 128, so (a | 0x80) - b cannot borrow across bytes; the xor restores the sign bit
+		return dot4_self(((a.v | 0x80808080u) - b.v) ^ 0x80808080u);
 	}
 };
-template <> struct Metric<kW0AVG> : LinearMetric<kW0AVG> { // ref :225-232, <= 5891
-	static S2TC_HD int dist(const FeatRGB &a, const FeatRGB &b)
-	{
-		int dr = a.r - b.r, dg = a.g - b.g, db = a.b - b.b;
-		return dr * dr + dg * dg + db * db;
-	}
-};
-template <> struct Metric<kWAVG> : LinearMetric<kWAVG> { // ref :234-241, <= 20681
-	static S2TC_HD int dist(const FeatRGB &a, const FeatRGB &b)
-	{
-		int dr = a.r - b.r, dg = a.g - b.g, db = a.b - b.b;
-		return ((dr * dr) << 2) + ((dg * dg) << 2) + db * db;
-	}
-};
+
+template <> struct Metric<kAVG> : SquareMetric<0x00FF00FFu> {};   // ref :217-223  4dr^2 +  dg^2 + 4db^2 <= 11657
+template <> struct Metric<kW0AVG> : SquareMetric<0x00000000u> {}; // ref :225-232   dr^2 +  dg^2 +  db^2 <= 5891
+template <> struct Metric<kWAVG> : SquareMetric<0x0000FFFFu> {};  // ref :234-241  4dr^2 + 4dg^2 +  db^2 <= 20681
 template <> struct Metric<kYUV> : LinearMetric<kYUV> { // ref :243-254
 	static S2TC_HD int dist(const FeatRGB &a, const FeatRGB &b)
 	{

@@ -326,23 +326,17 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, const 
 
 	// 3. distance matrix, columns zero-padded to 16 (ref :375-392; argument order matters for SRGB)
 	if constexpr (kPack) {
-		// AVG / WAVG / W0AVG are sums of squares of integer-weighted channel differences (weights 2,1,2 / 2,2,1 /
-		// 1,1,1): scale the channels once per colour, subtract all three per byte, square-and-add with one IDP.4A
-		constexpr uint32_t wr = CD == kW0AVG ? 1 : 2, wg = CD == kWAVG ? 2 : 1, wb = CD == kAVG ? 2 : 1;
-		uint32_t *cvec = reinterpret_cast<uint32_t *>(feat); // [mcap] scaled colours, bytes < 128
-		for (int i = lane; i < m; i += 32) {
-			const uint32_t c = col[i];
-			cvec[i] = (px_r(c) * wr) | ((px_g(c) * wg) << 8) | ((px_b(c) * wb) << 16);
-		}
+		// AVG / WAVG / W0AVG: the metric's feature is the colour with pre-scaled channel bytes and a distance is one
+		// per-byte subtraction + IDP.4A (colordist.cuh)
+		uint32_t *cvec = reinterpret_cast<uint32_t *>(feat); // [mcap]
+		for (int i = lane; i < m; i += 32)
+			cvec[i] = M::feat(col[i]).v;
 		__syncwarp();
 		for (int e = lane; e < mpad * 16; e += 32) {
 			const int i = e >> 4, k = e & 15;
 			int d = 0;
-			if (i < m && k < n) {
-				// per-byte difference without borrows: bytes of cvec are < 128, so (a | 0x80) - b stays within each byte
-				const uint32_t diff = ((cvec[i] | 0x80808080u) - cvec[k]) ^ 0x80808080u;
-				d = __dp4a((int) diff, (int) diff, 0);
-			}
+			if (i < m && k < n)
+				d = M::dist(FeatBytes{cvec[i]}, FeatBytes{cvec[k]});
 			reinterpret_cast<uint16_t *>(rows + i * kPitch)[k] = (uint16_t) d;
 		}
 	} else {
