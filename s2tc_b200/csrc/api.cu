@@ -72,7 +72,13 @@ struct PendingTiming {
 };
 
 constexpr int kPlanRing = 64;
-constexpr int kBlocksPerRandThread = 8;
+constexpr int kBlocksPerRandThreadDefault = 8;
+static int rand_bpt()
+{
+	static const int v = [] { const char *e = getenv("S2TC_B200_RAND_BPT"); int n = e ? atoi(e) : 0; return n > 0 && n <= 4096 ? n : kBlocksPerRandThreadDefault; }();
+	return v;
+}
+#define kBlocksPerRandThread rand_bpt()
 constexpr long long kSlabBlocks = 1 << 20; // MODE_NORMAL works through an image in slabs of at most this many blocks
 
 } // namespace
@@ -81,7 +87,7 @@ struct s2tc_b200_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
 	std::mutex mu;
-	DevBuf src, reduced, out, ends, cand_c, cand_a, dither_ws, plans, small, mip;
+	DevBuf src, reduced, out, ends, cand_c, cand_a, dither_ws, plans, small, mip, rand_ws;
 	RandPlan *h_plans = nullptr; // pinned ring
 	int plan_next = 0;
 	int *h_carry = nullptr; // pinned, 4 ints
@@ -173,8 +179,9 @@ int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &
 		c->plan_next++;
 		rand_plan_init(*hp, cursor0 + (uint64_t) blk0 * dpb, (uint64_t) kBlocksPerRandThread * dpb);
 		CU(cudaMemcpyAsync(dp, hp, sizeof(RandPlan), cudaMemcpyHostToDevice, st));
-		FamScope f(c, st, kFamCand, 1);
-		CU(launch_random_candidates(s.dxt, nrandom, v, dp, kBlocksPerRandThread, (uint16_t *) c->cand_c.p,
+		CU(c->rand_ws.reserve(random_candidates_workspace_bytes((size_t) nblocks, kBlocksPerRandThread)));
+		FamScope f(c, st, kFamCand, 2);
+		CU(launch_random_candidates(s.dxt, nrandom, v, dp, kBlocksPerRandThread, (uint32_t *) c->rand_ws.p, (uint16_t *) c->cand_c.p,
 				(uint8_t *) c->cand_a.p, st));
 	}
 	{
@@ -319,7 +326,7 @@ void s2tc_b200_ctx_destroy(s2tc_b200_ctx *c)
 		cudaEventDestroy(p.a);
 		cudaEventDestroy(p.b);
 	}
-	DevBuf *bufs[] = {&c->src, &c->reduced, &c->out, &c->ends, &c->cand_c, &c->cand_a, &c->dither_ws, &c->plans, &c->small, &c->mip};
+	DevBuf *bufs[] = {&c->src, &c->reduced, &c->out, &c->ends, &c->cand_c, &c->cand_a, &c->dither_ws, &c->plans, &c->small, &c->mip, &c->rand_ws};
 	for (DevBuf *b : bufs)
 		b->release();
 	cudaFreeHost(c->h_plans);

@@ -103,8 +103,10 @@ cudaError_t launch_fast_encode(int dxt, int cd, int refine, const ImageView &v, 
 
 // MODE_NORMAL step 1 (nrandom > 0): random candidate colours for every block of the view.
 // d_cand_c: [blocks][nrandom] uint16 (565), d_cand_a: [blocks][nrandom] uint8 (DXT5 only)
+// d_windows: workspace of random_candidates_workspace_bytes(blocks, blocks_per_thread)
+size_t random_candidates_workspace_bytes(size_t nblocks, int blocks_per_thread);
 cudaError_t launch_random_candidates(int dxt, int nrandom, const ImageView &v, const RandPlan *d_plan,
-		int blocks_per_thread, uint16_t *d_cand_c, uint8_t *d_cand_a, cudaStream_t stream);
+		int blocks_per_thread, uint32_t *d_windows, uint16_t *d_cand_c, uint8_t *d_cand_a, cudaStream_t stream);
 
 // MODE_NORMAL step 2: the c0/c1 (and DXT5 a0/a1) pair search, a thread group per block.
 // d_ends: [blocks] uint2 {c0_565 | c1_565 << 16, a0 | a1 << 8}
