@@ -115,6 +115,21 @@ def orc_compress(img, dxt, cd=WAVG, nrandom=-1, refine=ALWAYS, dither=DITHER_SIM
     return out
 
 
+def orc_rows(img, dxt, cd, nrandom, refine, dither, rows, cursor=0):
+    """Block rows [rows[0], rows[1]) of the whole-image encode: the pre-pass runs over the full image (the carry chain
+    needs it), only the requested block rows are searched.  Makes full-size spot checks affordable."""
+    img = np.ascontiguousarray(img)
+    h, w, comps = img.shape
+    L = lib()
+    L.orc_encode_block_rows.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_uint64, _u8p, C.c_int]
+    red = orc_prepass(img, {DXT1: 1, DXT3: 4, DXT5: 8}[dxt], dither)
+    bw = (w + 3) // 4
+    full = np.zeros(((h + 3) // 4) * bw * block_bytes(dxt), np.uint8)
+    L.orc_encode_block_rows(_ptr(red), w, h, rows[0], rows[1], dxt, cd, nrandom, refine, cursor, _ptr(full), 0)
+    return full[rows[0] * bw * block_bytes(dxt):rows[1] * bw * block_bytes(dxt)].copy()
+
+
 def orc_prepass(img, alphabits, dither):
     img = np.ascontiguousarray(img)
     h, w, comps = img.shape
