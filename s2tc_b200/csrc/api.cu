@@ -511,7 +511,7 @@ int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int
 	// instead of their sum.  The two pieces of cross-slab state stay on the device: the DITHER_SIMPLE carry
 	// (chained through d_carry on the compute stream) and the rand cursor (closed form per block row).
 	static const int slab_mb = [] { const char *e = getenv("S2TC_B200_SLAB_MB"); int n = e ? atoi(e) : 0; return n > 0 ? n : 16; }();
-	int nslab = (int) (in_bytes / ((size_t) slab_mb << 20)); // ~16 MiB of texels per slab by default (measured: 64/32/16/8 MiB -> e2e 6.3/5.9/5.5/7.2 ms on config 2)
+	int nslab = (int) (in_bytes / ((size_t) slab_mb << 20)); // ~16 MiB of texels per slab by default (measured on config 2: 32 / 16 / 8 MiB -> e2e 5.9 / 5.5 / 7.2 ms)
 	nslab = nslab < 1 ? 1 : (nslab > 64 ? 64 : nslab);
 	if (nslab > bh)
 		nslab = bh;
