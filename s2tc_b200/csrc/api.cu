@@ -155,15 +155,19 @@ int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &
 		return 0;
 	}
 	const int nrandom = s.nrandom > 0 ? s.nrandom : 0;
-	if (nrandom == 0) { // <= 16 candidates: the fused register-resident encoder
-		FamScope f(c, st, kFamSearch, 1);
-		CU(launch_encode16(s.dxt, s.cd, s.refine, v, d_dst, st));
+	CU(c->ends.reserve((size_t) nblocks * sizeof(uint2)));
+	if (nrandom == 0) { // <= 16 candidates: the register-resident search, then refinement + packing
+		{
+			FamScope f(c, st, kFamSearch, 1);
+			CU(launch_search16(s.dxt, s.cd, v, (uint2 *) c->ends.p, st));
+		}
+		FamScope f(c, st, kFamFinish, 1);
+		CU(launch_finish(s.dxt, s.cd, s.refine, v, (const uint2 *) c->ends.p, d_dst, st));
 		return 0;
 	}
 	if (nrandom > pair_search_max_nrandom())
 		return fail(S2TC_B200_EUNSUPPORTED, "S2TC_RANDOM_COLORS=%d exceeds the %d candidates the search kernel can hold in shared memory",
 				nrandom, pair_search_max_nrandom());
-	CU(c->ends.reserve((size_t) nblocks * sizeof(uint2)));
 	if (nrandom) {
 		CU(c->cand_c.reserve((size_t) nblocks * nrandom * sizeof(uint16_t)));
 		if (s.dxt == kDxt5)

@@ -115,16 +115,16 @@ cudaError_t launch_pair_search(int dxt, int cd, int nrandom, const ImageView &v,
 // largest nrandom the search kernel can hold in shared memory
 int pair_search_max_nrandom();
 
-// MODE_NORMAL with at most 16 candidates (nrandom <= 0): gather + search + refinement + packing fused,
-// one thread per block, the distance matrix in registers (search16.inl; one TU per DXT mode).
-cudaError_t launch_encode16_dxt1(int cd, int refine, const ImageView &v, void *d_out, cudaStream_t stream);
-cudaError_t launch_encode16_dxt3(int cd, int refine, const ImageView &v, void *d_out, cudaStream_t stream);
-cudaError_t launch_encode16_dxt5(int cd, int refine, const ImageView &v, void *d_out, cudaStream_t stream);
-inline cudaError_t launch_encode16(int dxt, int cd, int refine, const ImageView &v, void *d_out, cudaStream_t stream)
+// MODE_NORMAL with at most 16 candidates (nrandom <= 0): gather + colour search (+ DXT5 alpha search), one thread
+// per block, the distance matrix in registers (search16.inl; one TU per DXT mode).  Output as launch_pair_search.
+cudaError_t launch_search16_dxt1(int cd, const ImageView &v, uint2 *d_ends, cudaStream_t stream);
+cudaError_t launch_search16_dxt3(int cd, const ImageView &v, uint2 *d_ends, cudaStream_t stream);
+cudaError_t launch_search16_dxt5(int cd, const ImageView &v, uint2 *d_ends, cudaStream_t stream);
+inline cudaError_t launch_search16(int dxt, int cd, const ImageView &v, uint2 *d_ends, cudaStream_t stream)
 {
-	return dxt == kDxt1 ? launch_encode16_dxt1(cd, refine, v, d_out, stream)
-			: dxt == kDxt3 ? launch_encode16_dxt3(cd, refine, v, d_out, stream)
-			: launch_encode16_dxt5(cd, refine, v, d_out, stream);
+	return dxt == kDxt1 ? launch_search16_dxt1(cd, v, d_ends, stream)
+			: dxt == kDxt3 ? launch_search16_dxt3(cd, v, d_ends, stream)
+			: launch_search16_dxt5(cd, v, d_ends, stream);
 }
 
 // MODE_NORMAL step 3: refinement + packing from the searched endpoints, one thread per block.

@@ -130,11 +130,34 @@ template <> struct RowRegs<false> {
 // rank of pair (i, j), i < j < m, in the reference's lexicographic scan order
 __device__ __forceinline__ int pair_rank(int i, int j, int m) { return i * m - ((i * (i + 1)) >> 1) + (j - i - 1); }
 
+// sum_k min(a[k], b[k]) with every horizontal add done by IDP.2A: 8 VIMNMX.U16x2 on the ALU pipe, 8 IDP.2A on the FMA
+// pipe, nothing else (the ALU pipe bounds this kernel: 83 % busy against 25 % for the FMA pipe in profiles/r01g)
+__device__ __forceinline__ uint32_t pair_sum_idp(const uint32_t (&a)[8], const uint32_t (&b)[8])
+{
+	uint32_t s0 = 0, s1 = 0;
+#pragma unroll
+	for (int q = 0; q < 8; q += 2) {
+		s0 = __dp2a_lo(__vminu2(a[q], b[q]), 0x0101u, s0);
+		s1 = __dp2a_lo(__vminu2(a[q + 1], b[q + 1]), 0x0101u, s1);
+	}
+	return s0 + s1;
+}
+
+// a * b + c kept as an IMAD on the FMA pipe (b is a kernel argument the compiler cannot fold into a shift)
+__device__ __forceinline__ uint32_t mad_opaque(uint32_t a, uint32_t b, uint32_t c)
+{
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+
 // Fast scan for 16-bit rows whose sums stay below 2^SUMBITS and whose pair count fits the remaining bits:
 // every pair becomes the single key (sum << RANKBITS) | rank, so "first minimum in (i, j) order" is an unsigned
-// min.  Only diagonal tiles (i >= j possible) and the last tile column (j >= m possible) need a validity test.
-template <bool SUM3, int SUMBITS>
-__device__ __forceinline__ uint32_t scan_tiles_keyed(const uint32_t *rows, int m, int lane)
+// min.  Inside a tile a lane meets 8 rows i in increasing order, so there the key is (sum << 3) | t and the rank
+// is attached once per tile.  Only diagonal tiles (i >= j possible) and the last tile column (j >= m possible)
+// need a validity test.  eight: the integer 8, opaque (see mad_opaque).
+template <int SUMBITS>
+__device__ __forceinline__ uint32_t scan_tiles_keyed(const uint32_t *rows, int m, int lane, uint32_t eight)
 {
 	constexpr int kRankBits = 32 - SUMBITS;
 	const int jj = lane & 15, half = lane >> 4;
@@ -147,31 +170,32 @@ __device__ __forceinline__ uint32_t scan_tiles_keyed(const uint32_t *rows, int m
 		const bool jlive = j < m;
 		for (int a = 0; a < b; ++a) { // off-diagonal tiles: every i < j
 			const int i0 = 16 * a + 8 * half;
-			int rank = pair_rank(i0, j, m);
 			uint32_t tbest = 0xFFFFFFFFu;
 #pragma unroll
 			for (int t = 0; t < 8; ++t) {
 				RowRegs<true> ri;
 				ri.load(rows, i0 + t);
-				const uint32_t sum = (uint32_t) pair_sum_p16<SUM3>(ri.w, rj.w);
-				tbest = min(tbest, (sum << kRankBits) + (uint32_t) rank);
-				rank += m - (i0 + t) - 2; // rank(i+1, j) - rank(i, j)
+				tbest = min(tbest, mad_opaque(pair_sum_idp(ri.w, rj.w), eight, (uint32_t) t));
 			}
+			const int i = i0 + (int) (tbest & 7u);
+			const uint32_t key = ((tbest >> 3) << kRankBits) + (uint32_t) pair_rank(i, j, m);
 			if (jlive)
-				best = min(best, tbest);
+				best = min(best, key);
 		}
 		{ // diagonal tile: pairs with i < j only
 			const int i0 = 16 * b + 8 * half;
-			int rank = pair_rank(i0, j, m);
+			uint32_t tbest = 0xFFFFFFFFu;
 #pragma unroll
 			for (int t = 0; t < 8; ++t) {
 				RowRegs<true> ri;
 				ri.load(rows, i0 + t);
-				const uint32_t sum = (uint32_t) pair_sum_p16<SUM3>(ri.w, rj.w);
-				const uint32_t key = (sum << kRankBits) + (uint32_t) rank;
-				if (i0 + t < j && jlive)
-					best = min(best, key);
-				rank += m - (i0 + t) - 2;
+				const uint32_t key = mad_opaque(pair_sum_idp(ri.w, rj.w), eight, (uint32_t) t);
+				if (i0 + t < j)
+					tbest = min(tbest, key);
+			}
+			if (jlive && tbest != 0xFFFFFFFFu) {
+				const int i = i0 + (int) (tbest & 7u);
+				best = min(best, ((tbest >> 3) << kRankBits) + (uint32_t) pair_rank(i, j, m));
 			}
 		}
 	}
@@ -257,7 +281,7 @@ __device__ __forceinline__ uint32_t scan_tiles(const uint32_t *rows, int m, int 
 
 template <int DXT, int CD>
 __global__ void __launch_bounds__(kSearchThreads)
-pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, const uint16_t *__restrict__ cand_c,
+pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, uint32_t eight, const uint16_t *__restrict__ cand_c,
 		const uint8_t *__restrict__ cand_a, uint2 *__restrict__ ends)
 {
 	typedef Metric<CD> M;
@@ -356,7 +380,7 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, const 
 	// 4. colour pair scan
 	uint32_t cij;
 	if (kPack && m <= 128) // sums < 16 * 20681 < 2^19, at most 8128 pairs: (sum, rank) fits one word
-		cij = scan_tiles_keyed<true, 19>(rows, m, lane);
+		cij = scan_tiles_keyed<19>(rows, m, lane, eight);
 	else
 		cij = scan_tiles<kPack, true, M::kMayBeNegative>(rows, m, lane);
 	const uint32_t c0 = col[cij >> 16], c1 = col[cij & 0xFFFFu];
@@ -375,7 +399,7 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, const 
 		}
 		__syncwarp();
 		// alpha sums < 16 * 65025 < 2^20, up to 4095 pairs (m <= 90) for the keyed scan
-		const uint32_t aij = m <= 90 ? scan_tiles_keyed<false, 20>(rows, m, lane) : scan_tiles<true, false, false>(rows, m, lane);
+		const uint32_t aij = m <= 90 ? scan_tiles_keyed<20>(rows, m, lane, eight) : scan_tiles<true, false, false>(rows, m, lane);
 		a01 = (col[aij >> 16] >> 24) | ((col[aij & 0xFFFFu] >> 24) << 8);
 	}
 	if (lane == 0)
@@ -405,7 +429,7 @@ static cudaError_t launch_search_cd(int nrandom, const ImageView &v, const uint1
 			return e;
 	}
 	const dim3 block(kSearchThreads), grid((nblocks + kSearchWarps - 1) / kSearchWarps);
-	kern<<<grid, block, smem, stream>>>(v, nrandom, mcap, wb, cand_c, cand_a, ends);
+	kern<<<grid, block, smem, stream>>>(v, nrandom, mcap, wb, 8u, cand_c, cand_a, ends);
 	return cudaGetLastError();
 }
 

@@ -1,19 +1,25 @@
 // search16.inl -- MODE_NORMAL without random candidates (S2TC_RANDOM_COLORS = 0, or NORMALMAP with
-// the default -1): gather, distance matrix, c0/c1 pair search, DXT5 alpha search, refinement and packing
-// fused in ONE kernel, one thread per 4x4 block, everything in registers.
+// the default -1): gather, distance matrix, c0/c1 pair search and the DXT5 alpha search in ONE kernel,
+// one thread per 4x4 block, everything in registers.  It writes the chosen endpoints; finish_kernel
+// (kernels_finish.cu) refines and packs them.
 //
 // Reference path per block: s2tc_algorithm.cpp:938-959 (gather), :997-1001 (single-colour hack), :367-414
-// (reduce_colors_inplace), :416-478 (reduce_colors_inplace_2fixpoints), then :1010-1107.
+// (reduce_colors_inplace), :416-478 (reduce_colors_inplace_2fixpoints).
 //
 // Why this shape: with at most 16 candidates the search is 120 pairs x 16 texels.  A thread keeps the
-// 120 distinct distances of the symmetric matrix in registers (all loops fully unrolled, every index a
-// compile-time constant), so the scan is pure VIMNMX/IADD3 with no shared memory, no shuffles and no
-// synchronisation; 32 independent blocks per warp give the ILP.  Blocks with fewer than 16 colours
-// (DXT1 transparency, ragged edges) run the same code with the missing rows/columns zeroed and the
-// missing pairs masked, which is exactly what the reference's smaller loops compute.
-// The first version of this path (a 4-lane group per block with the matrix in shared memory, kept in
-// kernels_search.cu for nrandom > 0) issued 2.6 bank conflicts per LDS and sat at 41 % issue
-// utilisation; see profiles/r01a_pair_search_g4_config2.ncu.txt.
+// distance matrix in registers (all loops fully unrolled, every index a compile-time constant), so the
+// scan has no shared memory, no shuffles and no synchronisation; 32 independent blocks per warp give the
+// ILP.  Two code paths:
+//   * search_full -- every texel of every block of the warp is a candidate (n == 16): the common case,
+//     tuned for the pipes (see there);
+//   * search_any  -- fewer colours (DXT1 transparency, ragged edges): the same scan with the missing
+//     rows/columns zeroed and the missing pairs masked, which is exactly what the reference's smaller
+//     loops compute.
+// History (profiles/README.md): a 4-lane group per block with the matrix in shared memory issued 2.6 bank
+// conflicts per LDS (r01a, 9.7 ms on config 2); the first register-resident version fused refinement and
+// packing into the same kernel (3.1 ms): its scans sat at ~90 % ALU-pipe utilisation with an idle FMA
+// pipe, and its refinement tail ran at 3 warps per scheduler.  Moving the adds to the FMA pipe, 16-bit
+// packed alpha rows and the split into search + finish kernels brought it to 1.75 + 0.73 ms.
 #include <utility>
 
 #include "kernels.cuh"
@@ -102,62 +108,239 @@ __device__ __forceinline__ void fill120(int (&D)[120], int n, F dist, std::integ
 	((D[P] = pair_j(P) < n ? dist(std::integral_constant<int, pair_i(P)>{}, std::integral_constant<int, pair_j(P)>{}) : 0), ...);
 }
 
-#ifndef S2TC_ENCODE16_MINBLOCKS
-#define S2TC_ENCODE16_MINBLOCKS 3
+// ---- the common case: every texel of the block is a candidate (n == 16) in every lane of the warp -----------
+// No masking anywhere, and two changes that take work off the ALU pipe, which bounds the scans (ncu: ALU pipe ~90 %
+// busy inside the scans with the FMA pipe idle):
+//  * the 16-term sums accumulate through IMAD (m * one + s, `one` an opaque kernel argument equal to 1) in
+//    S2TC_ENCODE16_CHAINS independent chains (measured on config 2: 1 / 2 / 4 / 7 chains -> 1.99 / 1.93 / 1.75 / 1.72 ms)
+//    instead of IADD3 only: a pair costs 20 ALU + 7 FMA-pipe instructions instead of 24 ALU;
+//  * distances that fit 16 bits (alpha always; AVG / WAVG / W0AVG colours) are stored as full rows of 16-bit halves,
+//    the DXT5 fixed points folded in (min(d[i][k], fix[k]) is stored, as in kernels_search.cu): a pair is
+//    8 VIMNMX.U16x2 + 8 IDP.2A, and since the sums stay below 2^20 the whole acceptance rule is one unsigned min over
+//    keys (sum << 7) | pair_number ("first minimum in scan order", ref :393-410).
+#ifndef S2TC_ENCODE16_CHAINS
+#define S2TC_ENCODE16_CHAINS 7 // independent accumulation chains per pair sum
 #endif
+template <int CD> struct Fits16 { static constexpr bool value = CD == kAVG || CD == kWAVG || CD == kW0AVG; };
+
+// t-th texel column that contributes to pair (I, J): every column, or (SKIP) every column but I and J, whose terms are 0
+template <int I, int J, bool SKIP>
+__host__ __device__ constexpr int kth_col(int t)
+{
+	if (!SKIP)
+		return t;
+	int k = 0;
+	for (;; ++k) {
+		if (k == I || k == J)
+			continue;
+		if (t-- == 0)
+			return k;
+	}
+}
+
+// a * b + c that the compiler cannot see through (written as a * one + c it factors `one` out of the whole sum)
+__device__ __forceinline__ uint32_t mad_opaque(uint32_t a, uint32_t b, uint32_t c)
+{
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+
+template <int I, int J, bool SKIP, int... T>
+__device__ __forceinline__ int pair_sum_full(const int (&D)[120], uint32_t one, std::integer_sequence<int, T...>)
+{
+	uint32_t s[S2TC_ENCODE16_CHAINS];
+	auto term = [&](auto tc) {
+		constexpr int t = decltype(tc)::value;
+		constexpr int k = kth_col<I, J, SKIP>(t);
+		const uint32_t m = (uint32_t) min(sym<I, k>(D), sym<J, k>(D));
+		constexpr int ch = t % S2TC_ENCODE16_CHAINS;
+		if constexpr (t < S2TC_ENCODE16_CHAINS)
+			s[ch] = m;
+		else
+			s[ch] = mad_opaque(m, one, s[ch]);
+	};
+	(term(std::integral_constant<int, T>{}), ...);
+	// the partial sums meet in plain adds (IADD3): a tree of the same multiply-adds measured slower, it lengthens
+	// the live ranges until the matrix spills (2.13 vs 1.72 ms on config 2)
+	uint32_t r = s[0];
+#pragma unroll
+	for (int q = 1; q < S2TC_ENCODE16_CHAINS; ++q)
+		r += s[q];
+	return (int) r;
+}
+
+template <int P, bool MAY_BE_NEGATIVE>
+__device__ __forceinline__ void pair_step_full(const int (&D)[120], uint32_t one, int &best, uint32_t &bp)
+{
+	constexpr int I = pair_i(P), J = pair_j(P);
+	constexpr bool SKIP = !MAY_BE_NEGATIVE; // d[i][i] = 0 and distances >= 0: the self terms are 0
+	const int sum = pair_sum_full<I, J, SKIP>(D, one, std::make_integer_sequence<int, SKIP ? 14 : 16>{});
+	bool accept;
+	if constexpr (MAY_BE_NEGATIVE)
+		accept = best < 0 || sum < best; // verbatim (ref :404)
+	else
+		accept = (uint32_t) sum < (uint32_t) best; // the same rule for sums >= 0 (best starts at -1)
+	if (accept) {
+		best = sum;
+		bp = (uint32_t) P;
+	}
+}
+
+// returns the number of the winning pair in scan order
+template <bool MAY_BE_NEGATIVE, int... P>
+__device__ __forceinline__ uint32_t scan120_full(const int (&D)[120], uint32_t one, std::integer_sequence<int, P...>)
+{
+	int best = -1;
+	uint32_t bp = 0; // pair 0 = (0, 1), the reference's initial besti/bestj
+	(pair_step_full<P, MAY_BE_NEGATIVE>(D, one, best, bp), ...);
+	return bp;
+}
+
+template <class F, int... P>
+__device__ __forceinline__ void fill120_full_impl(int (&D)[120], F dist, std::integer_sequence<int, P...>)
+{
+	((D[P] = dist(std::integral_constant<int, pair_i(P)>{}, std::integral_constant<int, pair_j(P)>{})), ...);
+}
+
+// 16-bit rows: R[i][q] = {d[i][2q], d[i][2q+1]}
+template <int P>
+__device__ __forceinline__ void pair_step_packed(const uint32_t (&R)[16][8], uint32_t scale, uint32_t &best)
+{
+	constexpr int I = pair_i(P), J = pair_j(P);
+	uint32_t s0 = 0, s1 = 0;
+#pragma unroll
+	for (int q = 0; q < 8; q += 2) {
+		s0 = __dp2a_lo(__vminu2(R[I][q], R[J][q]), 0x0101u, s0);
+		s1 = __dp2a_lo(__vminu2(R[I][q + 1], R[J][q + 1]), 0x0101u, s1);
+	}
+	// key = (s0 + s1) * 128 + P; scale = 128 is opaque so that the two multiply-adds stay on the FMA pipe
+	best = min(best, mad_opaque(s0, scale, mad_opaque(s1, scale, (uint32_t) P)));
+}
+
+template <int... P>
+__device__ __forceinline__ uint32_t scan120_packed(const uint32_t (&R)[16][8], uint32_t scale, std::integer_sequence<int, P...>)
+{
+	uint32_t best = 0xFFFFFFFFu;
+	(pair_step_packed<P>(R, scale, best), ...);
+	return best & 127u;
+}
+
+// pair number -> (i << 4) | j
+__device__ __forceinline__ uint32_t pair_unrank(uint32_t p)
+{
+	uint32_t i = 0;
+	while (p >= 15u - i) {
+		p -= 15u - i;
+		++i;
+	}
+	return (i << 4) | (i + 1u + p);
+}
+
 template <int DXT, int CD>
-__global__ void __launch_bounds__(128, S2TC_ENCODE16_MINBLOCKS) encode16_kernel(ImageView v, int refine, uint8_t *out)
+__device__ __forceinline__ void search_full(const Block &b, uint32_t one, uint32_t &c0, uint32_t &c1, int &a0, int &a1)
 {
 	typedef Metric<CD> M;
 	typedef typename M::Feat Feat;
-	const int nblocks = v.blocks_w * v.blocks_h;
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= nblocks)
-		return;
-	const int by = t / v.blocks_w, bx = t - by * v.blocks_w;
-	Block b;
-	load_block(v, bx, by, b);
-
-	// ---- gather in the reference's column-major order (ref :940-959) --------------------------------
-	uint32_t usemask = 0; // bit o = x*4 + y
+	uint32_t cl[16]; // the candidates in the reference's column-major order (ref :940-951), addressable for the final reads
 #pragma unroll
-	for (int i = 0; i < 16; ++i) {
-		bool use = (b.valid >> i) & 1u;
-		if (DXT == kDxt1)
-			use = use && (b.px[i] >> 24) != 0;
-		if (use)
-			usemask |= 1u << ((i & 3) * 4 + (i >> 2));
+	for (int o = 0; o < 16; ++o)
+		cl[o] = b.px[(o & 3) * 4 + (o >> 2)];
+	const uint32_t scale = one << 7;
+
+	uint32_t bij;
+	if constexpr (Fits16<CD>::value) {
+		uint32_t R[16][8];
+#pragma unroll
+		for (int i = 0; i < 16; ++i)
+#pragma unroll
+			for (int q = 0; q < 8; ++q)
+				R[i][q] = 0;
+		{
+			Feat f[16];
+#pragma unroll
+			for (int k = 0; k < 16; ++k)
+				f[k] = M::feat(cl[k]);
+			// these metrics are symmetric: every distance is computed once and dropped into both rows
+#pragma unroll
+			for (int i = 0; i < 16; ++i)
+#pragma unroll
+				for (int k = i + 1; k < 16; ++k) {
+					const uint32_t d = (uint32_t) M::dist(f[i], f[k]);
+					R[i][k >> 1] += d << (16 * (k & 1));
+					R[k][i >> 1] += d << (16 * (i & 1));
+				}
+		}
+		bij = pair_unrank(scan120_packed(R, scale, std::make_integer_sequence<int, 120>{}));
+	} else {
+		int D[120];
+		{
+			Feat f[16];
+#pragma unroll
+			for (int k = 0; k < 16; ++k)
+				f[k] = M::feat(cl[k]);
+			// lower index first: SRGB is not symmetric
+			fill120_full_impl(D, [&](auto i, auto k) { return M::dist(f[decltype(i)::value], f[decltype(k)::value]); },
+					std::make_integer_sequence<int, 120>{});
+		}
+		bij = pair_unrank(scan120_full<M::kMayBeNegative>(D, one, std::make_integer_sequence<int, 120>{}));
 	}
+	c0 = px_rgb(cl[bij >> 4]);
+	c1 = px_rgb(cl[bij & 15u]);
+
+	a0 = a1 = 0;
+	if (DXT == kDxt5) { // ref :416-478
+		uint32_t R[16][8];
+		{
+			uint32_t a[16], fixw[8];
+#pragma unroll
+			for (int k = 0; k < 16; ++k)
+				a[k] = cl[k] >> 24; // re-read: the registers that held the texels are dead by now
+#pragma unroll
+			for (int q = 0; q < 8; ++q) {
+				const uint32_t x = a[2 * q], y = a[2 * q + 1];
+				fixw[q] = min(x * x, (255u - x) * (255u - x)) | (min(y * y, (255u - y) * (255u - y)) << 16);
+			}
+#pragma unroll
+			for (int i = 0; i < 16; ++i) {
+#pragma unroll
+				for (int q = 0; q < 8; ++q) {
+					const uint32_t t0 = a[i] - a[2 * q], t1 = (a[i] - a[2 * q + 1]) << 8; // wrapping: squares are exact mod 2^32
+					R[i][q] = __vminu2(t1 * t1 + t0 * t0, fixw[q]);
+				}
+			}
+		}
+		const uint32_t aij = pair_unrank(scan120_packed(R, scale, std::make_integer_sequence<int, 120>{}));
+		a0 = (int) (cl[aij >> 4] >> 24);
+		a1 = (int) (cl[aij & 15u] >> 24);
+	}
+}
+
+// ---- any n: DXT1 transparency, ragged edges ------------------------------------------------------------------
+template <int DXT, int CD>
+__device__ __noinline__ void search_any(const Block &b, uint32_t usemask, uint32_t &c0, uint32_t &c1, int &a0, int &a1)
+{
+	typedef Metric<CD> M;
+	typedef typename M::Feat Feat;
 	uint32_t c[16];
 	uint32_t cl[16]; // the same list, addressable (two dynamic reads after the search)
-	int n;
-	if (usemask == 0xFFFFu) {
+	int n = 0;
 #pragma unroll
-		for (int o = 0; o < 16; ++o)
-			c[o] = b.px[(o & 3) * 4 + (o >> 2)];
-		n = 16;
-	} else {
-		n = 0;
+	for (int o = 0; o < 16; ++o)
+		cl[o] = 0;
 #pragma unroll
-		for (int o = 0; o < 16; ++o)
-			cl[o] = 0;
-#pragma unroll
-		for (int o = 0; o < 16; ++o)
-			if ((usemask >> o) & 1u)
-				cl[n++] = b.px[(o & 3) * 4 + (o >> 2)];
-		if (n == 0)
-			n = 1; // black, alpha 0 (ref :952-959)
-		if (n == 1) { // ref :997-1001 (and see DESIGN.md on the reference's uninitialised ca[1])
-			cl[1] = cl[0];
-			n = 2;
-		}
-#pragma unroll
-		for (int o = 0; o < 16; ++o)
-			c[o] = cl[o];
+	for (int o = 0; o < 16; ++o)
+		if ((usemask >> o) & 1u)
+			cl[n++] = b.px[(o & 3) * 4 + (o >> 2)];
+	if (n == 0)
+		n = 1; // black, alpha 0 (ref :952-959)
+	if (n == 1) { // ref :997-1001 (and see DESIGN.md on the reference's uninitialised ca[1])
+		cl[1] = cl[0];
+		n = 2;
 	}
 #pragma unroll
 	for (int o = 0; o < 16; ++o)
-		cl[o] = c[o];
+		c[o] = cl[o];
 
 	// ---- colour distance matrix: the 120 entries above the diagonal (ref :375-383) -----------------
 	int D[120];
@@ -177,88 +360,94 @@ __global__ void __launch_bounds__(128, S2TC_ENCODE16_MINBLOCKS) encode16_kernel(
 
 	// ---- pair scan in lexicographic (i, j) order (ref :393-410) ---------------------------------------
 	const uint32_t bij = scan120<M::kMayBeNegative, false>(D, fix, n, std::make_integer_sequence<int, 120>{});
-	const uint32_t c0 = px_rgb(cl[bij >> 4]), c1 = px_rgb(cl[bij & 15u]);
+	c0 = px_rgb(cl[bij >> 4]);
+	c1 = px_rgb(cl[bij & 15u]);
 
 	// ---- DXT5: the same search on alpha with the fixed points 0 and 255 (ref :416-478) ----------------
-	int a0 = 0, a1 = 0;
+	a0 = a1 = 0;
 	if (DXT == kDxt5) {
 		int a[16];
-		bool flat = true; // every gathered alpha equal
 #pragma unroll
-		for (int k = 0; k < 16; ++k) {
-			a[k] = (int) (cl[k] >> 24); // re-read: c[] is dead by now, which keeps the scan's live set at the matrix itself
-			flat = flat && (k >= n || a[k] == a[0]);
-		}
-		// Exact shortcut: with a single alpha value every distance is 0, every pair sums to 0, and the reference keeps
-		// its first pair (0,1) (ref :467-477).  Measured on config 2 (75 % flat blocks, 32 % flat warps) it made the kernel
-		// SLOWER (4.21 ms vs 3.11 ms without it, same box, A/B builds), so it is off unless S2TC_ENCODE16_FLAT_ALPHA is
-		// defined; the split into two branches is kept because it removed the DXT5 register spills (3.57 -> 3.11 ms).
-#ifndef S2TC_ENCODE16_FLAT_ALPHA
-		flat = false;
-#endif
-		if (__all_sync(__activemask(), flat)) {
-			a0 = a[0];
-			a1 = a[1];
-		} else {
+		for (int k = 0; k < 16; ++k)
+			a[k] = (int) (cl[k] >> 24);
 #pragma unroll
-			for (int k = 0; k < 16; ++k)
-				fix[k] = k < n ? min(a[k] * a[k], (255 - a[k]) * (255 - a[k])) : 0;
-			fill120(D, n, [&](auto i, auto k) {
-				const int d = a[decltype(i)::value] - a[decltype(k)::value];
-				return d * d;
-			}, std::make_integer_sequence<int, 120>{});
-			const uint32_t aij = scan120<false, true>(D, fix, n, std::make_integer_sequence<int, 120>{});
-			a0 = (int) (cl[aij >> 4] >> 24);
-			a1 = (int) (cl[aij & 15u] >> 24);
-		}
+		for (int k = 0; k < 16; ++k)
+			fix[k] = k < n ? min(a[k] * a[k], (255 - a[k]) * (255 - a[k])) : 0;
+		fill120(D, n, [&](auto i, auto k) {
+			const int d = a[decltype(i)::value] - a[decltype(k)::value];
+			return d * d;
+		}, std::make_integer_sequence<int, 120>{});
+		const uint32_t aij = scan120<false, true>(D, fix, n, std::make_integer_sequence<int, 120>{});
+		a0 = (int) (cl[aij >> 4] >> 24);
+		a1 = (int) (cl[aij & 15u] >> 24);
 	}
+}
 
-	// ---- refinement and packing (ref :1010-1107) ---------------------------------------------------------
-	// the texels are read again (L1/L2 hits) instead of being kept live across the two scans: the scans need
-	// 120 registers for the matrix alone
+#ifndef S2TC_ENCODE16_MINBLOCKS
+#define S2TC_ENCODE16_MINBLOCKS 3
+#endif
+constexpr int kSearch16Threads = 128;
+// Writes the chosen endpoints of every block, {c0 | c1 << 16 as RGB565, a0 | a1 << 8}, the layout finish_kernel
+// reads.  one: the integer 1 (see search_full).
+template <int DXT, int CD>
+__global__ void __launch_bounds__(kSearch16Threads, S2TC_ENCODE16_MINBLOCKS) search16_kernel(ImageView v, uint32_t one, uint2 *__restrict__ ends)
+{
+	const int nblocks = v.blocks_w * v.blocks_h;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= nblocks)
+		return;
+	const int by = t / v.blocks_w, bx = t - by * v.blocks_w;
+	Block b;
 	load_block(v, bx, by, b);
-	uint32_t w[4];
-	finish_block<DXT, CD>(b, refine, c0, c1, a0, a1, w);
-	if (DXT == kDxt1)
-		reinterpret_cast<uint2 *>(out)[t] = make_uint2(w[0], w[1]);
+
+	// ---- which texels are candidates, in the reference's column-major order (ref :940-959) ---------------
+	uint32_t usemask = 0; // bit o = x*4 + y
+#pragma unroll
+	for (int i = 0; i < 16; ++i) {
+		bool use = (b.valid >> i) & 1u;
+		if (DXT == kDxt1)
+			use = use && (b.px[i] >> 24) != 0;
+		if (use)
+			usemask |= 1u << ((i & 3) * 4 + (i >> 2));
+	}
+	uint32_t c0, c1;
+	int a0, a1;
+	if (__all_sync(__activemask(), usemask == 0xFFFFu)) // warp-uniform
+		search_full<DXT, CD>(b, one, c0, c1, a0, a1);
 	else
-		reinterpret_cast<uint4 *>(out)[t] = make_uint4(w[0], w[1], w[2], w[3]);
+		search_any<DXT, CD>(b, usemask, c0, c1, a0, a1);
+	ends[t] = make_uint2(to565(c0) | (to565(c1) << 16), (uint32_t) a0 | ((uint32_t) a1 << 8));
 }
 
 template <int DXT>
-static cudaError_t launch_encode16_dxt(int cd, int refine, const ImageView &v, void *d_out, cudaStream_t stream)
+static cudaError_t launch_search16_dxt(int cd, const ImageView &v, uint2 *d_ends, cudaStream_t stream)
 {
 	const int nblocks = v.blocks_w * v.blocks_h;
 	if (nblocks == 0)
 		return cudaSuccess;
-	const dim3 block(128), grid((nblocks + 127) / 128);
-	uint8_t *out = (uint8_t *) d_out;
+	const dim3 block(kSearch16Threads), grid((nblocks + kSearch16Threads - 1) / kSearch16Threads);
 	switch (cd) {
-#ifdef S2TC_ENCODE16_ONLY_CD
-	case S2TC_ENCODE16_ONLY_CD: encode16_kernel<DXT, S2TC_ENCODE16_ONLY_CD><<<grid, block, 0, stream>>>(v, refine, out); break;
-	default: return cudaErrorInvalidValue;
-	}
-	return cudaGetLastError();
-}
+#ifdef S2TC_ENCODE16_ONLY_CD // A/B builds of a single metric (see the Makefile's EXTRA)
+	case S2TC_ENCODE16_ONLY_CD: search16_kernel<DXT, S2TC_ENCODE16_ONLY_CD><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
 #else
-	case kRGB: encode16_kernel<DXT, kRGB><<<grid, block, 0, stream>>>(v, refine, out); break;
-	case kYUV: encode16_kernel<DXT, kYUV><<<grid, block, 0, stream>>>(v, refine, out); break;
-	case kSRGB: encode16_kernel<DXT, kSRGB><<<grid, block, 0, stream>>>(v, refine, out); break;
-	case kSRGB_MIXED: encode16_kernel<DXT, kSRGB_MIXED><<<grid, block, 0, stream>>>(v, refine, out); break;
-	case kAVG: encode16_kernel<DXT, kAVG><<<grid, block, 0, stream>>>(v, refine, out); break;
-	case kWAVG: encode16_kernel<DXT, kWAVG><<<grid, block, 0, stream>>>(v, refine, out); break;
-	case kW0AVG: encode16_kernel<DXT, kW0AVG><<<grid, block, 0, stream>>>(v, refine, out); break;
-	case kNORMALMAP: encode16_kernel<DXT, kNORMALMAP><<<grid, block, 0, stream>>>(v, refine, out); break;
+	case kRGB: search16_kernel<DXT, kRGB><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
+	case kYUV: search16_kernel<DXT, kYUV><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
+	case kSRGB: search16_kernel<DXT, kSRGB><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
+	case kSRGB_MIXED: search16_kernel<DXT, kSRGB_MIXED><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
+	case kAVG: search16_kernel<DXT, kAVG><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
+	case kWAVG: search16_kernel<DXT, kWAVG><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
+	case kW0AVG: search16_kernel<DXT, kW0AVG><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
+	case kNORMALMAP: search16_kernel<DXT, kNORMALMAP><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
+#endif
 	default: return cudaErrorInvalidValue;
 	}
 	return cudaGetLastError();
 }
-#endif
 
 // one translation unit per DXT mode (the fully unrolled scans are slow to compile)
-cudaError_t S2TC_ENCODE16_NAME(int cd, int refine, const ImageView &v, void *d_out, cudaStream_t stream)
+cudaError_t S2TC_ENCODE16_NAME(int cd, const ImageView &v, uint2 *d_ends, cudaStream_t stream)
 {
-	return launch_encode16_dxt<S2TC_ENCODE16_DXT>(cd, refine, v, d_out, stream);
+	return launch_search16_dxt<S2TC_ENCODE16_DXT>(cd, v, d_ends, stream);
 }
 
 } // namespace s2tc
