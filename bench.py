@@ -334,6 +334,9 @@ def main():
     dom_ms, dom_n = fam[dom]
     if dom == "prepass":
         dom_n //= 3   # the three phases of the carry scan are timed as one group
+    search_group = 2 if (nrandom <= 0 and st.dxt == 2) else 1   # search16 runs DXT5 as a colour launch + an alpha launch
+    if dom == "search":
+        dom_n //= search_group
     dom_ms_launch = dom_ms / max(dom_n, 1)
     per_launch_blocks = blocks * args.steps / max(dom_n, 1)
     # algorithmic bytes per block the kernel must move: 64 B of texels in, the kernel's result out
@@ -343,12 +346,13 @@ def main():
     int32_peak = enc.int32_peak_gops()
     n_pairs = (16 + max(nrandom, 0)) * (15 + max(nrandom, 0)) // 2
     int_ops_block = n_pairs * 16 * 2 * (2 if st.dxt == 2 else 1)   # min + add per (pair, texel); DXT5 searches alpha too
-    search_ms = fam["search"][0] / max(fam["search"][1], 1)
-    search_blocks = blocks * args.steps / max(fam["search"][1], 1)
+    search_n = fam["search"][1] // search_group
+    search_ms = fam["search"][0] / max(search_n, 1)
+    search_blocks = blocks * args.steps / max(search_n, 1)
     int32 = None
     if fam["search"][1]:
         a = int_ops_block * search_blocks / (search_ms * 1e-3) / 1e9
-        int32 = {"kernel": "pair_search", "achieved": a, "peak": int32_peak, "unit": "Gop/s (int32 min+add)",
+        int32 = {"kernel": "pair_search_kernel" if nrandom > 0 else "search16_kernel", "achieved": a, "peak": int32_peak, "unit": "Gop/s (int32 min+add)",
                  "frac": a / int32_peak if int32_peak else None,
                  "ops_per_block": int_ops_block, "peak_source": "measured in this run (s2tc_b200_int32_peak)"}
     traffic = None

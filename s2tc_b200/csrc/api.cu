@@ -79,7 +79,7 @@ static int rand_bpt()
 	return v;
 }
 #define kBlocksPerRandThread rand_bpt()
-constexpr long long kSlabBlocks = 1 << 20; // MODE_NORMAL works through an image in slabs of at most this many blocks
+constexpr long long kSlabBlocks = 1 << 22; // MODE_NORMAL works through an image in slabs of at most this many blocks
 
 } // namespace
 
@@ -158,7 +158,7 @@ int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &
 	CU(c->ends.reserve((size_t) nblocks * sizeof(uint2)));
 	if (nrandom == 0) { // <= 16 candidates: the register-resident search, then refinement + packing
 		{
-			FamScope f(c, st, kFamSearch, 1);
+			FamScope f(c, st, kFamSearch, s.dxt == kDxt5 ? 2 : 1); // DXT5: colour launch + alpha launch
 			CU(launch_search16(s.dxt, s.cd, v, (uint2 *) c->ends.p, st));
 		}
 		FamScope f(c, st, kFamFinish, 1);

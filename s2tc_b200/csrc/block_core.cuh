@@ -367,6 +367,10 @@ S2TC_HD uint32_t refine_colors(const Block &b, int refine, uint32_t use, uint32_
 				next0 = mean_color(tot - s1n, n0);
 			if (n1)
 				next1 = mean_color(s1n, n1);
+			// fixed point: the next pass would assign identically, score the same and stop on "not <" without
+			// changing anything (ref :781-793), so it is not run
+			if (next0 == c0 && next1 == c1)
+				break;
 		}
 	}
 
@@ -461,6 +465,8 @@ S2TC_HD uint64_t refine_alpha(const Block &b, int refine, int &a0, int &a1)
 					next0 = mean_alpha(p.s0, p.n0);
 				if (p.n1)
 					next1 = mean_alpha(p.s1, p.n1);
+				if (next0 == a0 && next1 == a1) // fixed point, as in refine_colors
+					break;
 			}
 		}
 		if (a1 == a0) { // ref :673-685: codes 1 -> 0

@@ -6,8 +6,11 @@
 
 namespace s2tc {
 
+#ifndef S2TC_FINISH_MINBLOCKS
+#define S2TC_FINISH_MINBLOCKS 6 // 80 registers: measured 4 / 6 / 8 CTAs per SM -> 0.66 / 0.63 / 0.70 ms on config 2 (8 spills)
+#endif
 template <int DXT, int CD>
-__global__ void __launch_bounds__(128) finish_kernel(ImageView v, int refine, const uint2 *__restrict__ ends, uint8_t *out)
+__global__ void __launch_bounds__(128, S2TC_FINISH_MINBLOCKS) finish_kernel(ImageView v, int refine, const uint2 *__restrict__ ends, uint8_t *out)
 {
 	const int nblocks = v.blocks_w * v.blocks_h;
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -130,19 +130,6 @@ template <> struct RowRegs<false> {
 // rank of pair (i, j), i < j < m, in the reference's lexicographic scan order
 __device__ __forceinline__ int pair_rank(int i, int j, int m) { return i * m - ((i * (i + 1)) >> 1) + (j - i - 1); }
 
-// sum_k min(a[k], b[k]) with every horizontal add done by IDP.2A: 8 VIMNMX.U16x2 on the ALU pipe, 8 IDP.2A on the FMA
-// pipe, nothing else (the ALU pipe bounds this kernel: 83 % busy against 25 % for the FMA pipe in profiles/r01g)
-__device__ __forceinline__ uint32_t pair_sum_idp(const uint32_t (&a)[8], const uint32_t (&b)[8])
-{
-	uint32_t s0 = 0, s1 = 0;
-#pragma unroll
-	for (int q = 0; q < 8; q += 2) {
-		s0 = __dp2a_lo(__vminu2(a[q], b[q]), 0x0101u, s0);
-		s1 = __dp2a_lo(__vminu2(a[q + 1], b[q + 1]), 0x0101u, s1);
-	}
-	return s0 + s1;
-}
-
 // a * b + c kept as an IMAD on the FMA pipe (b is a kernel argument the compiler cannot fold into a shift)
 __device__ __forceinline__ uint32_t mad_opaque(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -151,59 +138,91 @@ __device__ __forceinline__ uint32_t mad_opaque(uint32_t a, uint32_t b, uint32_t 
 	return d;
 }
 
+// Tile-local pair key (sum_k min(a[k], b[k]) << 3) | t.  Every horizontal add is an IDP.2A: 8 VIMNMX.U16x2 on the ALU
+// pipe, 8 IDP.2A + 1 IMAD on the FMA pipe, nothing else.  (With packed IADD3 adds in front of 3 IDP.2A the ALU pipe
+// bounded the kernel: 83 % busy against 25 % for the FMA pipe, profiles/r01g; this form is issue-bound, r01h.)
+__device__ __forceinline__ uint32_t pair_key(const uint32_t (&a)[8], const uint32_t (&b)[8], uint32_t eight, int t)
+{
+	uint32_t s = 0;
+#pragma unroll
+	for (int q = 0; q < 8; ++q)
+		s = __dp2a_lo(__vminu2(a[q], b[q]), 0x0101u, s);
+	return mad_opaque(s, eight, (uint32_t) t);
+}
+
 // Fast scan for 16-bit rows whose sums stay below 2^SUMBITS and whose pair count fits the remaining bits:
 // every pair becomes the single key (sum << RANKBITS) | rank, so "first minimum in (i, j) order" is an unsigned
 // min.  Inside a tile a lane meets 8 rows i in increasing order, so there the key is (sum << 3) | t and the rank
-// is attached once per tile.  Only diagonal tiles (i >= j possible) and the last tile column (j >= m possible)
-// need a validity test.  eight: the integer 8, opaque (see mad_opaque).
+// is attached once per tile.  Tile columns are taken two at a time (a lane keeps rows j and j + 16 in registers), so
+// that one broadcast load of row i serves two pairs.  Only diagonal tiles (i >= j possible) and the last tile column
+// (j >= m possible) need a validity test.  eight: the integer 8, opaque (see mad_opaque).
+template <int SUMBITS> struct KeyedScan {
+	static constexpr int kRankBits = 32 - SUMBITS;
+	const uint32_t *rows;
+	int m, jj, half;
+	uint32_t eight;
+	uint32_t best = 0xFFFFFFFFu;
+
+	__device__ __forceinline__ void fold(uint32_t tbest, int i0, int j)
+	{
+		if (j < m && tbest != 0xFFFFFFFFu) {
+			const int i = i0 + (int) (tbest & 7u);
+			best = min(best, ((tbest >> 3) << kRankBits) + (uint32_t) pair_rank(i, j, m));
+		}
+	}
+	// tile row a against tile column(s) whose lane rows are r1 (row j1) and, if TWO, r2 (row j1 + 16); DIAG1 / DIAG2:
+	// the tile is the diagonal one of that column, only i < j counts
+	template <bool TWO, bool DIAG1, bool DIAG2>
+	__device__ __forceinline__ void tile(int a, const RowRegs<true> &r1, const RowRegs<true> &r2, int j1)
+	{
+		const int i0 = 16 * a + 8 * half;
+		uint32_t t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu;
+#pragma unroll
+		for (int t = 0; t < 8; ++t) {
+			RowRegs<true> ri;
+			ri.load(rows, i0 + t);
+			const uint32_t k1 = pair_key(ri.w, r1.w, eight, t);
+			if (!DIAG1 || i0 + t < j1)
+				t1 = min(t1, k1);
+			if (TWO) {
+				const uint32_t k2 = pair_key(ri.w, r2.w, eight, t);
+				if (!DIAG2 || i0 + t < j1 + 16)
+					t2 = min(t2, k2);
+			}
+		}
+		fold(t1, i0, j1);
+		if (TWO)
+			fold(t2, i0, j1 + 16);
+	}
+};
+
 template <int SUMBITS>
 __device__ __forceinline__ uint32_t scan_tiles_keyed(const uint32_t *rows, int m, int lane, uint32_t eight)
 {
-	constexpr int kRankBits = 32 - SUMBITS;
-	const int jj = lane & 15, half = lane >> 4;
+	KeyedScan<SUMBITS> ks{rows, m, lane & 15, lane >> 4, eight};
 	const int ntile = (m + 15) >> 4;
-	uint32_t best = 0xFFFFFFFFu;
-	for (int b = 0; b < ntile; ++b) {
-		const int j = 16 * b + jj;
-		RowRegs<true> rj;
-		rj.load(rows, j);
-		const bool jlive = j < m;
-		for (int a = 0; a < b; ++a) { // off-diagonal tiles: every i < j
-			const int i0 = 16 * a + 8 * half;
-			uint32_t tbest = 0xFFFFFFFFu;
-#pragma unroll
-			for (int t = 0; t < 8; ++t) {
-				RowRegs<true> ri;
-				ri.load(rows, i0 + t);
-				tbest = min(tbest, mad_opaque(pair_sum_idp(ri.w, rj.w), eight, (uint32_t) t));
-			}
-			const int i = i0 + (int) (tbest & 7u);
-			const uint32_t key = ((tbest >> 3) << kRankBits) + (uint32_t) pair_rank(i, j, m);
-			if (jlive)
-				best = min(best, key);
-		}
-		{ // diagonal tile: pairs with i < j only
-			const int i0 = 16 * b + 8 * half;
-			uint32_t tbest = 0xFFFFFFFFu;
-#pragma unroll
-			for (int t = 0; t < 8; ++t) {
-				RowRegs<true> ri;
-				ri.load(rows, i0 + t);
-				const uint32_t key = mad_opaque(pair_sum_idp(ri.w, rj.w), eight, (uint32_t) t);
-				if (i0 + t < j)
-					tbest = min(tbest, key);
-			}
-			if (jlive && tbest != 0xFFFFFFFFu) {
-				const int i = i0 + (int) (tbest & 7u);
-				best = min(best, ((tbest >> 3) << kRankBits) + (uint32_t) pair_rank(i, j, m));
-			}
-		}
+	int b = ntile - 1; // columns from the right, in pairs (b - 1, b); column 0 stays single when ntile is odd
+	for (; b >= 1; b -= 2) {
+		const int j1 = 16 * (b - 1) + ks.jj;
+		RowRegs<true> r1, r2;
+		r1.load(rows, j1);
+		r2.load(rows, j1 + 16);
+		for (int a = 0; a < b - 1; ++a)
+			ks.template tile<true, false, false>(a, r1, r2, j1);
+		ks.template tile<true, true, false>(b - 1, r1, r2, j1); // diagonal of column b - 1, off-diagonal of column b
+		ks.template tile<false, true, false>(b, r2, r2, j1 + 16); // diagonal of column b
 	}
+	if (b == 0) {
+		RowRegs<true> r1;
+		r1.load(rows, ks.jj);
+		ks.template tile<false, true, false>(0, r1, r1, ks.jj);
+	}
+	uint32_t best = ks.best;
 #pragma unroll
 	for (int off = 16; off > 0; off >>= 1)
 		best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, off));
 	// rank -> (i, j): walk the row starts (m <= 128 rows, uniform across the warp)
-	int rank = (int) (best & ((1u << kRankBits) - 1u)), i = 0;
+	int rank = (int) (best & ((1u << KeyedScan<SUMBITS>::kRankBits) - 1u)), i = 0;
 	while (rank >= m - 1 - i) {
 		rank -= m - 1 - i;
 		++i;
@@ -356,22 +375,31 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, uint32
 		for (int i = lane; i < m; i += 32)
 			cvec[i] = M::feat(col[i]).v;
 		__syncwarp();
-		for (int e = lane; e < mpad * 16; e += 32) {
-			const int i = e >> 4, k = e & 15;
-			int d = 0;
-			if (i < m && k < n)
-				d = M::dist(FeatBytes{cvec[i]}, FeatBytes{cvec[k]});
-			reinterpret_cast<uint16_t *>(rows + i * kPitch)[k] = (uint16_t) d;
+		// lane -> one packed word per row (texel columns 2kq, 2kq+1), 4 rows per step; everything the lane needs from its
+		// columns is loop-invariant.  Reads of cvec beyond m return leftovers that the masks discard.
+		const int kq = lane & 7;
+		const uint32_t ck0 = cvec[2 * kq], ck1 = cvec[2 * kq + 1];
+		const uint32_t kmask = (2 * kq < n ? 0x0000FFFFu : 0u) | (2 * kq + 1 < n ? 0xFFFF0000u : 0u);
+#pragma unroll 2
+		for (int i = lane >> 3; i < mpad; i += 4) {
+			const uint32_t ci = cvec[i];
+			const uint32_t d0 = (uint32_t) M::dist(FeatBytes{ci}, FeatBytes{ck0}), d1 = (uint32_t) M::dist(FeatBytes{ci}, FeatBytes{ck1});
+			rows[i * kPitch + kq] = i < m ? ((d0 | (d1 << 16)) & kmask) : 0u;
 		}
 	} else {
 		for (int i = lane; i < m; i += 32)
 			feat[i] = M::feat(col[i]);
 		__syncwarp();
-		for (int e = lane; e < mpad * 16; e += 32) {
-			const int i = e >> 4, k = e & 15;
+		// lane -> texel column k, 2 rows per step
+		const int k = lane & 15;
+		const Feat fk = feat[k];
+		const bool kok = k < n;
+		for (int i = lane >> 4; i < mpad; i += 2) {
 			int d = 0;
-			if (i < m && k < n && k != i)
-				d = (i < n && k < i) ? M::dist(feat[k], feat[i]) : M::dist(feat[i], feat[k]);
+			if (i < m && kok && k != i) {
+				const Feat fi = feat[i];
+				d = (i < n && k < i) ? M::dist(fk, fi) : M::dist(fi, fk);
+			}
 			rows[i * kPitch + k] = (uint32_t) d;
 		}
 	}
@@ -388,14 +416,17 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, uint32
 
 	if (DXT == kDxt5) { // ref :416-478; alpha rows are always 16-bit, at the 16-bit pitch inside the same buffer
 		__syncwarp();
-		for (int e = lane; e < mpad * 16; e += 32) {
-			const int i = e >> 4, k = e & 15;
-			int d = 0;
-			if (i < m && k < n) {
-				const int ak = (int) (col[k] >> 24), ai = (int) (col[i] >> 24);
-				d = min((ai - ak) * (ai - ak), min(ak * ak, (255 - ak) * (255 - ak)));
+		{ // the fixed points 0 and 255 folded into every row: min(d[i][k], fix[k]) is stored (masked columns: fix = 0)
+			const int kq = lane & 7;
+			const uint32_t ak0 = col[2 * kq] >> 24, ak1 = col[2 * kq + 1] >> 24;
+			const uint32_t f0 = min(ak0 * ak0, (255u - ak0) * (255u - ak0)), f1 = min(ak1 * ak1, (255u - ak1) * (255u - ak1));
+			const uint32_t fixw = (2 * kq < n ? f0 : 0u) | (2 * kq + 1 < n ? f1 << 16 : 0u);
+#pragma unroll 2
+			for (int i = lane >> 3; i < mpad; i += 4) {
+				const uint32_t ai = col[i] >> 24;
+				const uint32_t t0 = ai - ak0, t1 = (ai - ak1) << 8; // wrapping: the squares are exact mod 2^32
+				rows[i * kPitch16 + kq] = i < m ? __vminu2(t1 * t1 + t0 * t0, fixw) : 0u;
 			}
-			reinterpret_cast<uint16_t *>(rows + i * kPitch16)[k] = (uint16_t) d;
 		}
 		__syncwarp();
 		// alpha sums < 16 * 65025 < 2^20, up to 4095 pairs (m <= 90) for the keyed scan

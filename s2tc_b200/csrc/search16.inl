@@ -237,7 +237,8 @@ __device__ __forceinline__ uint32_t pair_unrank(uint32_t p)
 	return (i << 4) | (i + 1u + p);
 }
 
-template <int DXT, int CD>
+// COLOR / ALPHA: which of the two searches to run (the kernel is launched once per search, see search16_kernel)
+template <int DXT, int CD, bool COLOR, bool ALPHA>
 __device__ __forceinline__ void search_full(const Block &b, uint32_t one, uint32_t &c0, uint32_t &c1, int &a0, int &a1)
 {
 	typedef Metric<CD> M;
@@ -248,6 +249,8 @@ __device__ __forceinline__ void search_full(const Block &b, uint32_t one, uint32
 		cl[o] = b.px[(o & 3) * 4 + (o >> 2)];
 	const uint32_t scale = one << 7;
 
+	c0 = c1 = 0;
+	if constexpr (COLOR) {
 	uint32_t bij;
 	if constexpr (Fits16<CD>::value) {
 		uint32_t R[16][8];
@@ -287,9 +290,10 @@ __device__ __forceinline__ void search_full(const Block &b, uint32_t one, uint32
 	}
 	c0 = px_rgb(cl[bij >> 4]);
 	c1 = px_rgb(cl[bij & 15u]);
+	}
 
 	a0 = a1 = 0;
-	if (DXT == kDxt5) { // ref :416-478
+	if constexpr (ALPHA && DXT == kDxt5) { // ref :416-478
 		uint32_t R[16][8];
 		{
 			uint32_t a[16], fixw[8];
@@ -317,7 +321,7 @@ __device__ __forceinline__ void search_full(const Block &b, uint32_t one, uint32
 }
 
 // ---- any n: DXT1 transparency, ragged edges ------------------------------------------------------------------
-template <int DXT, int CD>
+template <int DXT, int CD, bool COLOR, bool ALPHA>
 __device__ __noinline__ void search_any(const Block &b, uint32_t usemask, uint32_t &c0, uint32_t &c1, int &a0, int &a1)
 {
 	typedef Metric<CD> M;
@@ -348,24 +352,26 @@ __device__ __noinline__ void search_any(const Block &b, uint32_t usemask, uint32
 #pragma unroll
 	for (int k = 0; k < 16; ++k)
 		fix[k] = 0;
-	{
-		Feat f[16];
+	c0 = c1 = 0;
+	if constexpr (COLOR) {
+		{
+			Feat f[16];
 #pragma unroll
-		for (int k = 0; k < 16; ++k)
-			f[k] = M::feat(c[k]);
-		// lower index first: SRGB is not symmetric
-		fill120(D, n, [&](auto i, auto k) { return M::dist(f[decltype(i)::value], f[decltype(k)::value]); },
-				std::make_integer_sequence<int, 120>{});
+			for (int k = 0; k < 16; ++k)
+				f[k] = M::feat(c[k]);
+			// lower index first: SRGB is not symmetric
+			fill120(D, n, [&](auto i, auto k) { return M::dist(f[decltype(i)::value], f[decltype(k)::value]); },
+					std::make_integer_sequence<int, 120>{});
+		}
+		// ---- pair scan in lexicographic (i, j) order (ref :393-410) ---------------------------------------
+		const uint32_t bij = scan120<M::kMayBeNegative, false>(D, fix, n, std::make_integer_sequence<int, 120>{});
+		c0 = px_rgb(cl[bij >> 4]);
+		c1 = px_rgb(cl[bij & 15u]);
 	}
-
-	// ---- pair scan in lexicographic (i, j) order (ref :393-410) ---------------------------------------
-	const uint32_t bij = scan120<M::kMayBeNegative, false>(D, fix, n, std::make_integer_sequence<int, 120>{});
-	c0 = px_rgb(cl[bij >> 4]);
-	c1 = px_rgb(cl[bij & 15u]);
 
 	// ---- DXT5: the same search on alpha with the fixed points 0 and 255 (ref :416-478) ----------------
 	a0 = a1 = 0;
-	if (DXT == kDxt5) {
+	if constexpr (ALPHA && DXT == kDxt5) {
 		int a[16];
 #pragma unroll
 		for (int k = 0; k < 16; ++k)
@@ -389,7 +395,9 @@ __device__ __noinline__ void search_any(const Block &b, uint32_t usemask, uint32
 constexpr int kSearch16Threads = 128;
 // Writes the chosen endpoints of every block, {c0 | c1 << 16 as RGB565, a0 | a1 << 8}, the layout finish_kernel
 // reads.  one: the integer 1 (see search_full).
-template <int DXT, int CD>
+// DXT5 runs it twice, once per search (COLOR writes the first word, ALPHA the second): each launch walks ~100 KB /
+// ~65 KB of straight-line code instead of ~150 KB in one kernel.  The alpha launch does not depend on the metric.
+template <int DXT, int CD, bool COLOR, bool ALPHA>
 __global__ void __launch_bounds__(kSearch16Threads, S2TC_ENCODE16_MINBLOCKS) search16_kernel(ImageView v, uint32_t one, uint2 *__restrict__ ends)
 {
 	const int nblocks = v.blocks_w * v.blocks_h;
@@ -413,10 +421,28 @@ __global__ void __launch_bounds__(kSearch16Threads, S2TC_ENCODE16_MINBLOCKS) sea
 	uint32_t c0, c1;
 	int a0, a1;
 	if (__all_sync(__activemask(), usemask == 0xFFFFu)) // warp-uniform
-		search_full<DXT, CD>(b, one, c0, c1, a0, a1);
+		search_full<DXT, CD, COLOR, ALPHA>(b, one, c0, c1, a0, a1);
 	else
-		search_any<DXT, CD>(b, usemask, c0, c1, a0, a1);
-	ends[t] = make_uint2(to565(c0) | (to565(c1) << 16), (uint32_t) a0 | ((uint32_t) a1 << 8));
+		search_any<DXT, CD, COLOR, ALPHA>(b, usemask, c0, c1, a0, a1);
+	const uint32_t cw = to565(c0) | (to565(c1) << 16), aw = (uint32_t) a0 | ((uint32_t) a1 << 8);
+	if (COLOR && (ALPHA || DXT != kDxt5))
+		ends[t] = make_uint2(cw, aw);
+	else if (COLOR)
+		ends[t].x = cw;
+	else
+		ends[t].y = aw;
+}
+
+template <int DXT, int CD>
+static void launch_search16_cd(dim3 grid, dim3 block, const ImageView &v, uint2 *d_ends, cudaStream_t stream)
+{
+#ifdef S2TC_SEARCH16_ONE_LAUNCH // A/B: both searches in one kernel
+	search16_kernel<DXT, CD, true, true><<<grid, block, 0, stream>>>(v, 1u, d_ends);
+#else
+	search16_kernel<DXT, CD, true, false><<<grid, block, 0, stream>>>(v, 1u, d_ends);
+	if (DXT == kDxt5)
+		search16_kernel<DXT, kRGB, false, true><<<grid, block, 0, stream>>>(v, 1u, d_ends);
+#endif
 }
 
 template <int DXT>
@@ -428,16 +454,16 @@ static cudaError_t launch_search16_dxt(int cd, const ImageView &v, uint2 *d_ends
 	const dim3 block(kSearch16Threads), grid((nblocks + kSearch16Threads - 1) / kSearch16Threads);
 	switch (cd) {
 #ifdef S2TC_ENCODE16_ONLY_CD // A/B builds of a single metric (see the Makefile's EXTRA)
-	case S2TC_ENCODE16_ONLY_CD: search16_kernel<DXT, S2TC_ENCODE16_ONLY_CD><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
+	case S2TC_ENCODE16_ONLY_CD: launch_search16_cd<DXT, S2TC_ENCODE16_ONLY_CD>(grid, block, v, d_ends, stream); break;
 #else
-	case kRGB: search16_kernel<DXT, kRGB><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
-	case kYUV: search16_kernel<DXT, kYUV><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
-	case kSRGB: search16_kernel<DXT, kSRGB><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
-	case kSRGB_MIXED: search16_kernel<DXT, kSRGB_MIXED><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
-	case kAVG: search16_kernel<DXT, kAVG><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
-	case kWAVG: search16_kernel<DXT, kWAVG><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
-	case kW0AVG: search16_kernel<DXT, kW0AVG><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
-	case kNORMALMAP: search16_kernel<DXT, kNORMALMAP><<<grid, block, 0, stream>>>(v, 1u, d_ends); break;
+	case kRGB: launch_search16_cd<DXT, kRGB>(grid, block, v, d_ends, stream); break;
+	case kYUV: launch_search16_cd<DXT, kYUV>(grid, block, v, d_ends, stream); break;
+	case kSRGB: launch_search16_cd<DXT, kSRGB>(grid, block, v, d_ends, stream); break;
+	case kSRGB_MIXED: launch_search16_cd<DXT, kSRGB_MIXED>(grid, block, v, d_ends, stream); break;
+	case kAVG: launch_search16_cd<DXT, kAVG>(grid, block, v, d_ends, stream); break;
+	case kWAVG: launch_search16_cd<DXT, kWAVG>(grid, block, v, d_ends, stream); break;
+	case kW0AVG: launch_search16_cd<DXT, kW0AVG>(grid, block, v, d_ends, stream); break;
+	case kNORMALMAP: launch_search16_cd<DXT, kNORMALMAP>(grid, block, v, d_ends, stream); break;
 #endif
 	default: return cudaErrorInvalidValue;
 	}
