@@ -343,18 +343,28 @@ def main():
     alg_bytes = {"fast": 64 + bs, "search": 64 + 8, "finish": 64 + 8 + bs, "prepass": 64 + 64, "candidates": 64 + nrandom * 2,
                  "transcode": 2 * bs}[dom]
     achieved = alg_bytes * per_launch_blocks / (dom_ms_launch * 1e-3) / 1e9 if dom_ms_launch > 0 else 0.0
-    int32_peak = enc.int32_peak_gops()
+    # integer roofline of the pair search: one min + one add per (pair, texel), for colours and -- DXT5 --
+    # once more for alpha.  Rows whose distances fit 16 bits (alpha; the AVG-family metrics) are scanned two texels per
+    # instruction, so their share is rated against the packed peak: peak = ops / (ops32 / R_scalar + ops16 / R_packed).
+    peak_scalar, peak_packed = enc.int_peaks_gops()
     n_pairs = (16 + max(nrandom, 0)) * (15 + max(nrandom, 0)) // 2
-    int_ops_block = n_pairs * 16 * 2 * (2 if st.dxt == 2 else 1)   # min + add per (pair, texel); DXT5 searches alpha too
+    colour_ops = n_pairs * 16 * 2
+    colour16 = cd_n in ("AVG", "WAVG", "W0AVG")
+    ops32 = 0 if colour16 else colour_ops
+    ops16 = (colour_ops if colour16 else 0) + (colour_ops if st.dxt == 2 else 0)
+    int_ops_block = ops32 + ops16
     search_n = fam["search"][1] // search_group
     search_ms = fam["search"][0] / max(search_n, 1)
     search_blocks = blocks * args.steps / max(search_n, 1)
     int32 = None
-    if fam["search"][1]:
+    if fam["search"][1] and peak_scalar and peak_packed:
         a = int_ops_block * search_blocks / (search_ms * 1e-3) / 1e9
-        int32 = {"kernel": "pair_search_kernel" if nrandom > 0 else "search16_kernel", "achieved": a, "peak": int32_peak, "unit": "Gop/s (int32 min+add)",
-                 "frac": a / int32_peak if int32_peak else None,
-                 "ops_per_block": int_ops_block, "peak_source": "measured in this run (s2tc_b200_int32_peak)"}
+        peak = int_ops_block / (ops32 / peak_scalar + ops16 / peak_packed)
+        int32 = {"kernel": "pair_search_kernel" if nrandom > 0 else "search16_kernel", "achieved": a, "peak": peak,
+                 "unit": "Gop/s (integer min+add)", "frac": a / peak,
+                 "ops_per_block": int_ops_block, "ops_per_block_32bit": ops32, "ops_per_block_16bit_packed": ops16,
+                 "peak_scalar": peak_scalar, "peak_packed16": peak_packed,
+                 "peak_source": "measured in this run (s2tc_b200_int_peaks: VIMNMX + IMAD on two pipes; VIMNMX.U16x2 + IDP.2A)"}
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:

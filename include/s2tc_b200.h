@@ -153,7 +153,10 @@ uint64_t s2tc_b200_launch_count(s2tc_b200_ctx *ctx);
 int s2tc_b200_profile_enable(s2tc_b200_ctx *ctx, int on);
 int s2tc_b200_profile_read(s2tc_b200_ctx *ctx, double ms[6], uint64_t launches[6], int reset);
 
-/* sustained INT32 (min + add) rate of the device in Gop/s: roofline denominator of the search kernels */
+/* sustained integer (min + add) rates of the device in Gop/s, the roofline denominators of the search kernels:
+ * scalar 32-bit operands (best of the compiler's own mix and VIMNMX + IMAD on two pipes), and 16-bit operands packed
+ * two to a register (VIMNMX.U16x2 + IDP.2A).  s2tc_b200_int32_peak returns the scalar one. */
+int s2tc_b200_int_peaks(s2tc_b200_ctx *ctx, double *scalar_gops, double *packed16_gops);
 int s2tc_b200_int32_peak(s2tc_b200_ctx *ctx, double *gops);
 
 #ifdef __cplusplus

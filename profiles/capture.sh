@@ -13,14 +13,15 @@ launches() { # name, bench args
 full() { # name, kernel regex, skip, count, bench args
 	$NCU --set full --import-source on -k regex:"$2" -s $3 -c $4 -f -o /tmp/prof_$1 python bench.py ${@:5} --steps 1 --kernel-only --no-check > /dev/null 2>&1
 	python profiles/ncu_summary.py /tmp/prof_$1.ncu-rep > $OUT/$1.ncu.txt 2>&1
+	python profiles/ncu_source.py /tmp/prof_$1.ncu-rep 32 > $OUT/$1.source.txt 2>&1
 	rm -f /tmp/prof_$1.ncu-rep
 }
 launches config2
-full config2_encode16 encode16 3 1
+full config2_search16_finish "search16|finish_kernel" 9 3
 launches config3_4096 --workload config3 --size 4096
 full config3_search_cand_finish "pair_search|random_cand|finish_kernel" 3 3 --workload config3 --size 4096
 launches defaults --workload defaults
 full defaults_fast_dither "fast_encode|dither_" 4 4 --workload defaults
 launches config5 --workload config5
-full config5_encode16_normalmap encode16 3 1 --workload config5
+full config5_search16_finish "search16|finish_kernel" 9 3 --workload config5
 ls -la $OUT

@@ -155,6 +155,7 @@ def lib():
     L.s2tc_b200_profile_enable.argtypes = [vp, i32]
     L.s2tc_b200_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64), i32]
     L.s2tc_b200_int32_peak.argtypes = [vp, C.POINTER(C.c_double)]
+    L.s2tc_b200_int_peaks.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.tx_compress_dxtn.argtypes = [i32, i32, i32, vp, C.c_uint, vp, i32]
     L.tx_compress_dxtn.restype = None
     L.rgb565_image.argtypes = [vp, vp, i32, i32, i32, i32, i32]
@@ -334,6 +335,12 @@ class Encoder:
         g = C.c_double()
         _check(lib().s2tc_b200_int32_peak(self._ctx, C.byref(g)))
         return g.value
+
+    def int_peaks_gops(self):
+        """(scalar 32-bit, 16-bit packed) sustained min+add rates in Gop/s"""
+        a, b = C.c_double(), C.c_double()
+        _check(lib().s2tc_b200_int_peaks(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def profile(self, on=True):
         _check(lib().s2tc_b200_profile_enable(self._ctx, 1 if on else 0))

@@ -838,12 +838,8 @@ int s2tc_b200_sync(s2tc_b200_ctx *c)
 
 uint64_t s2tc_b200_launch_count(s2tc_b200_ctx *c) { return c ? c->launches : 0; }
 
-int s2tc_b200_int32_peak(s2tc_b200_ctx *c, double *gops)
+static int int_peak_mode(s2tc_b200_ctx *c, int mode, double ops_per_step, double *gops)
 {
-	if (!c || !gops)
-		return fail(S2TC_B200_EINVAL, "NULL argument");
-	std::lock_guard<std::mutex> lock(c->mu);
-	CU(cudaSetDevice(c->device));
 	const int iters = 1 << 14, ctas = 148 * 16;
 	int *sink = (int *) c->small.p + 200;
 	cudaEvent_t a, b;
@@ -852,12 +848,12 @@ int s2tc_b200_int32_peak(s2tc_b200_ctx *c, double *gops)
 	double best = 0;
 	for (int rep = 0; rep < 4; ++rep) { // first repetition warms up
 		CU(cudaEventRecord(a, c->stream));
-		CU(launch_int32_peak(iters, ctas, sink, c->stream));
+		CU(launch_int32_peak(mode, iters, ctas, sink, c->stream));
 		CU(cudaEventRecord(b, c->stream));
 		CU(cudaEventSynchronize(b));
 		float ms = 0;
 		CU(cudaEventElapsedTime(&ms, a, b));
-		const double ops = 2.0 * 8.0 * iters * 256.0 * ctas;
+		const double ops = ops_per_step * 8.0 * iters * 256.0 * ctas;
 		if (rep && ms > 0 && ops / ms * 1e-6 > best)
 			best = ops / ms * 1e-6;
 	}
@@ -865,6 +861,27 @@ int s2tc_b200_int32_peak(s2tc_b200_ctx *c, double *gops)
 	cudaEventDestroy(b);
 	*gops = best;
 	return 0;
+}
+
+int s2tc_b200_int_peaks(s2tc_b200_ctx *c, double *scalar_gops, double *packed16_gops)
+{
+	if (!c || !scalar_gops || !packed16_gops)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	double plain = 0, dual = 0;
+	if (int rc = int_peak_mode(c, 0, 2.0, &plain))
+		return rc;
+	if (int rc = int_peak_mode(c, 1, 2.0, &dual))
+		return rc;
+	*scalar_gops = plain > dual ? plain : dual;
+	return int_peak_mode(c, 2, 4.0, packed16_gops);
+}
+
+int s2tc_b200_int32_peak(s2tc_b200_ctx *c, double *gops)
+{
+	double packed;
+	return s2tc_b200_int_peaks(c, gops, &packed);
 }
 
 int s2tc_b200_profile_enable(s2tc_b200_ctx *c, int on)

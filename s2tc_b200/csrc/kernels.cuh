@@ -161,7 +161,7 @@ cudaError_t launch_decode(int dxt, const void *d_blocks, int width, int height, 
 // S3TC -> S2TC transcode, in place.
 cudaError_t launch_transcode(int dxt, void *d_blocks, size_t nblocks, cudaStream_t stream);
 
-// measurement aid: `ctas` CTAs of 256 threads each run iters * 8 (min, add) pairs per thread
-cudaError_t launch_int32_peak(int iters, int ctas, int *d_sink, cudaStream_t stream);
+// measurement aid: `ctas` CTAs of 256 threads each run iters * 8 (min, add) pairs per thread; mode: see kernels_misc.cu
+cudaError_t launch_int32_peak(int mode, int iters, int ctas, int *d_sink, cudaStream_t stream);
 
 } // namespace s2tc

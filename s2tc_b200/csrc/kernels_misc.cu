@@ -848,36 +848,52 @@ cudaError_t launch_decode(int dxt, const void *d_blocks, int width, int height, 
 }
 
 // =====================================================================================================
-// Measurement aid: sustained INT32 min+add issue rate, the denominator for the search kernels' roofline
-// (search modes are bound by the integer pipes, not by HBM).  8 independent chains per
-// thread of exactly the two operations the pair scan is made of (IMNMX + IADD).
+// Measurement aid: sustained integer min+add rate, the denominator for the search kernels' roofline
+// (search modes are bound by the integer pipes, not by HBM).  8 independent chains per thread of
+// exactly the two operations the pair scan is made of, in the three instruction mixes the kernels use:
+//   MODE 0  s += min(a, b)                       as the compiler schedules it (VIMNMX + IADD3, mostly the ALU pipe)
+//   MODE 1  s = min(a, b) * one + s              VIMNMX on the ALU pipe, IMAD on the FMA pipe (search16's 32-bit scan)
+//   MODE 2  s = dp2a(vminu2(a, b), 0x0101, s)    VIMNMX.U16x2 + IDP.2A: two mins and two adds per instruction pair
+//                                                (the 16-bit packed rows of search16 and pair_search)
 // =====================================================================================================
-__global__ void __launch_bounds__(256) int32_peak_kernel(int iters, int seed, int *sink)
+template <int MODE>
+__global__ void __launch_bounds__(256) int32_peak_kernel(int iters, int seed, uint32_t one, int *sink)
 {
-	int a[8], s[8];
+	uint32_t a[8], s[8];
 #pragma unroll
 	for (int k = 0; k < 8; ++k) {
-		a[k] = seed + threadIdx.x * (k + 1);
+		a[k] = (uint32_t) (seed + threadIdx.x * (k + 1)) & 0x3FFF3FFFu;
 		s[k] = 0;
 	}
-	int b = seed ^ (blockIdx.x << 8);
+	uint32_t b = (uint32_t) (seed ^ (blockIdx.x << 8)) & 0x3FFF3FFFu;
 	for (int i = 0; i < iters; ++i) {
 #pragma unroll
-		for (int k = 0; k < 8; ++k)
-			s[k] += min(a[k], b); // the pair scan's inner operation: accumulate the smaller distance
-		b += 3;
+		for (int k = 0; k < 8; ++k) {
+			if (MODE == 0)
+				s[k] += min(a[k], b);
+			else if (MODE == 1)
+				asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(s[k]) : "r"(min(a[k], b)), "r"(one));
+			else
+				s[k] = __dp2a_lo(__vminu2(a[k], b), 0x0101u, s[k]);
+		}
+		b = (b + 3u) & 0x3FFF3FFFu;
 	}
-	int r = 0;
+	uint32_t r = 0;
 #pragma unroll
 	for (int k = 0; k < 8; ++k)
 		r ^= s[k];
-	if (r == 0x7FFFFFFF)
-		*sink = r;
+	if (r == 0x7FFFFFFFu)
+		*sink = (int) r;
 }
 
-cudaError_t launch_int32_peak(int iters, int ctas, int *d_sink, cudaStream_t stream)
+cudaError_t launch_int32_peak(int mode, int iters, int ctas, int *d_sink, cudaStream_t stream)
 {
-	int32_peak_kernel<<<ctas, 256, 0, stream>>>(iters, 12345, d_sink);
+	if (mode == 0)
+		int32_peak_kernel<0><<<ctas, 256, 0, stream>>>(iters, 12345, 1u, d_sink);
+	else if (mode == 1)
+		int32_peak_kernel<1><<<ctas, 256, 0, stream>>>(iters, 12345, 1u, d_sink);
+	else
+		int32_peak_kernel<2><<<ctas, 256, 0, stream>>>(iters, 12345, 1u, d_sink);
 	return cudaGetLastError();
 }
 

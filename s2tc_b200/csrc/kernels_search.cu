@@ -152,82 +152,107 @@ __device__ __forceinline__ uint32_t pair_key(const uint32_t (&a)[8], const uint3
 
 // Fast scan for 16-bit rows whose sums stay below 2^SUMBITS and whose pair count fits the remaining bits:
 // every pair becomes the single key (sum << RANKBITS) | rank, so "first minimum in (i, j) order" is an unsigned
-// min.  Inside a tile a lane meets 8 rows i in increasing order, so there the key is (sum << 3) | t and the rank
-// is attached once per tile.  Tile columns are taken two at a time (a lane keeps rows j and j + 16 in registers), so
-// that one broadcast load of row i serves two pairs.  Only diagonal tiles (i >= j possible) and the last tile column
-// (j >= m possible) need a validity test.  eight: the integer 8, opaque (see mad_opaque).
+// min.  The pair triangle is cut into 16x16 tiles.
+//   * Off-diagonal tiles (every i < j): lane (jj, half) keeps row j of the tile column in registers and meets the 8 rows
+//     i = 16a + 8 half + t in increasing order, so inside a tile the key is (sum << 3) | t and the rank is attached
+//     once per tile.  Tile columns are taken two at a time (rows j and j + 16 in registers), so that one broadcast
+//     load of row i serves two pairs.
+//   * Diagonal tiles hold 120 pairs: 4 per lane, both rows loaded per pair (the (jj, half) walk would spend 8 steps
+//     per lane on them at 47 % utilisation).
+// Only the last tile column can hold rows j >= m.  eight: the integer 8, opaque (see mad_opaque).
 template <int SUMBITS> struct KeyedScan {
 	static constexpr int kRankBits = 32 - SUMBITS;
 	const uint32_t *rows;
-	int m, jj, half;
+	int m, lane;
 	uint32_t eight;
 	uint32_t best = 0xFFFFFFFFu;
 
-	__device__ __forceinline__ void fold(uint32_t tbest, int i0, int j)
-	{
-		if (j < m && tbest != 0xFFFFFFFFu) {
-			const int i = i0 + (int) (tbest & 7u);
-			best = min(best, ((tbest >> 3) << kRankBits) + (uint32_t) pair_rank(i, j, m));
-		}
-	}
-	// tile row a against tile column(s) whose lane rows are r1 (row j1) and, if TWO, r2 (row j1 + 16); DIAG1 / DIAG2:
-	// the tile is the diagonal one of that column, only i < j counts
-	template <bool TWO, bool DIAG1, bool DIAG2>
+	// tile row a against tile column(s) whose lane rows are r1 (row j1) and, if TWO, r2 (row j1 + 16)
+	template <bool TWO>
 	__device__ __forceinline__ void tile(int a, const RowRegs<true> &r1, const RowRegs<true> &r2, int j1)
 	{
-		const int i0 = 16 * a + 8 * half;
+		const int i0 = 16 * a + 8 * (lane >> 4);
 		uint32_t t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu;
 #pragma unroll
 		for (int t = 0; t < 8; ++t) {
 			RowRegs<true> ri;
 			ri.load(rows, i0 + t);
-			const uint32_t k1 = pair_key(ri.w, r1.w, eight, t);
-			if (!DIAG1 || i0 + t < j1)
-				t1 = min(t1, k1);
-			if (TWO) {
-				const uint32_t k2 = pair_key(ri.w, r2.w, eight, t);
-				if (!DIAG2 || i0 + t < j1 + 16)
-					t2 = min(t2, k2);
-			}
+			t1 = min(t1, pair_key(ri.w, r1.w, eight, t));
+			if (TWO)
+				t2 = min(t2, pair_key(ri.w, r2.w, eight, t));
 		}
-		fold(t1, i0, j1);
-		if (TWO)
-			fold(t2, i0, j1 + 16);
+		if (j1 < m)
+			best = min(best, ((t1 >> 3) << kRankBits) + (uint32_t) pair_rank(i0 + (int) (t1 & 7u), j1, m));
+		if (TWO && j1 + 16 < m)
+			best = min(best, ((t2 >> 3) << kRankBits) + (uint32_t) pair_rank(i0 + (int) (t2 & 7u), j1 + 16, m));
+	}
+
+	// pairs number lane, lane + 32, lane + 64, lane + 96 (< 120) of diagonal tile b, numbered in lexicographic order
+	__device__ __forceinline__ void diagonal(int b, const uint32_t (&dij)[4])
+	{
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const int i = 16 * b + (int) (dij[q] & 0xFFu), j = 16 * b + (int) (dij[q] >> 8);
+			RowRegs<true> ri, rj;
+			ri.load(rows, i);
+			rj.load(rows, j);
+			uint32_t sum = 0;
+#pragma unroll
+			for (int w = 0; w < 8; ++w)
+				sum = __dp2a_lo(__vminu2(ri.w[w], rj.w[w]), 0x0101u, sum);
+			if ((q < 3 || lane < 24) && j < m)
+				best = min(best, (sum << kRankBits) + (uint32_t) pair_rank(i, j, m));
+		}
 	}
 };
 
 template <int SUMBITS>
 __device__ __forceinline__ uint32_t scan_tiles_keyed(const uint32_t *rows, int m, int lane, uint32_t eight)
 {
-	KeyedScan<SUMBITS> ks{rows, m, lane & 15, lane >> 4, eight};
+	KeyedScan<SUMBITS> ks{rows, m, lane, eight};
 	const int ntile = (m + 15) >> 4;
-	int b = ntile - 1; // columns from the right, in pairs (b - 1, b); column 0 stays single when ntile is odd
-	for (; b >= 1; b -= 2) {
-		const int j1 = 16 * (b - 1) + ks.jj;
+	const int jj = lane & 15;
+	// off-diagonal tiles, columns from the right in pairs (b - 1, b)
+	for (int b = ntile - 1; b >= 1; b -= 2) {
+		const int j1 = 16 * (b - 1) + jj;
 		RowRegs<true> r1, r2;
 		r1.load(rows, j1);
 		r2.load(rows, j1 + 16);
 		for (int a = 0; a < b - 1; ++a)
-			ks.template tile<true, false, false>(a, r1, r2, j1);
-		ks.template tile<true, true, false>(b - 1, r1, r2, j1); // diagonal of column b - 1, off-diagonal of column b
-		ks.template tile<false, true, false>(b, r2, r2, j1 + 16); // diagonal of column b
+			ks.template tile<true>(a, r1, r2, j1);
+		ks.template tile<false>(b - 1, r2, r2, j1 + 16); // tile row b - 1 is off-diagonal for column b only
 	}
-	if (b == 0) {
-		RowRegs<true> r1;
-		r1.load(rows, ks.jj);
-		ks.template tile<false, true, false>(0, r1, r1, ks.jj);
+	// diagonal tiles
+	uint32_t dij[4]; // i | j << 8 inside a tile
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		int p = lane + 32 * q, i = 0;
+		if (p >= 120)
+			p = 0; // lanes 24..31 have no fourth pair: any valid pair, masked in diagonal()
+		while (p >= 15 - i) {
+			p -= 15 - i;
+			++i;
+		}
+		dij[q] = (uint32_t) i | ((uint32_t) (i + 1 + p) << 8);
 	}
+	for (int b = 0; b < ntile; ++b)
+		ks.diagonal(b, dij);
 	uint32_t best = ks.best;
 #pragma unroll
 	for (int off = 16; off > 0; off >>= 1)
 		best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, off));
-	// rank -> (i, j): walk the row starts (m <= 128 rows, uniform across the warp)
-	int rank = (int) (best & ((1u << KeyedScan<SUMBITS>::kRankBits) - 1u)), i = 0;
-	while (rank >= m - 1 - i) {
-		rank -= m - 1 - i;
-		++i;
+	// rank -> (i, j): row i of the pair order starts at rank i (m - 1) - i (i - 1) / 2; every lane tests four rows
+	// (m <= 128) and the one that holds the rank announces itself
+	const int rank = (int) (best & ((1u << KeyedScan<SUMBITS>::kRankBits) - 1u));
+	uint32_t mine = 0;
+#pragma unroll
+	for (int q = 0; q < 4; ++q) {
+		const int i = lane + 32 * q;
+		const int start = i * (m - 1) - ((i * (i - 1)) >> 1);
+		if (i < m - 1 && rank >= start && rank < start + (m - 1 - i))
+			mine = ((uint32_t) i << 16) | (uint32_t) (i + 1 + rank - start);
 	}
-	return ((uint32_t) i << 16) | (uint32_t) (i + 1 + rank);
+	return __reduce_or_sync(0xFFFFFFFFu, mine);
 }
 
 // Generic scan: any row width, any sum range.  Returns (i << 16) | j of the winner in every lane.
