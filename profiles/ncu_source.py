@@ -38,6 +38,10 @@ def main():
         stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
         tot = sum(int(r[S]) for r in data) or 1
         warps = int(data[0][IE]) or 1   # the first instruction is executed once by every warp
+        sig = (name, len(data), tot)
+        if sig == getattr(main, "last", None):   # ncu lists some results twice
+            continue
+        main.last = sig
         print(f"=== {name[:110]}")
         print(f"    {len(data)} SASS instructions, {sum(int(r[IE]) for r in data) / warps:.0f} executed per warp, {tot} stall samples")
         allst = collections.Counter()

@@ -54,6 +54,66 @@ constexpr int kChunk = 128;       // texels per thread
 constexpr int kTileThreads = 128; // chunks per CTA
 constexpr int kTilePixels = kChunk * kTileThreads;
 
+static_assert(kTileThreads == 128, "one warp per channel walks the chunk carries");
+
+// Walks one channel through the tile's 128 chunk maps: s_carry[i * 4 + ch] = carry entering chunk i; returns the carry
+// after the last chunk.  Called by ONE lane per channel, each in a different warp: the kinds are different code
+// paths, and a warp that ran them in four of its lanes serialised them (the walk was a third of the apply kernel's
+// time, profiles/r01h).  Shift kinds stay in table-index form, the 1-bit kind in biased-residue form, so a step is
+// one dependent shared-memory load.
+__device__ __forceinline__ int walk_chunk_carries(const ByteMap *s_maps, int *s_carry, int ch, int kind, int c)
+{
+	if (kind <= kChanShift4) {
+		const int r = chan_radius(kind);
+		uint32_t idx = (uint32_t) (c + r);
+#pragma unroll 4
+		for (int i = 0; i < kTileThreads; ++i) {
+			s_carry[i * 4 + ch] = (int) idx - r;
+			idx = s_maps[i * 4 + ch].e[idx];
+		}
+		return (int) idx - r;
+	}
+	if (kind == kChanBit1) { // balanced255(c + sum): keep u = c + 127 in [0, 254]
+		uint32_t u = (uint32_t) (c + 127);
+#pragma unroll 4
+		for (int i = 0; i < kTileThreads; ++i) {
+			s_carry[i * 4 + ch] = (int) u - 127;
+			u += s_maps[i * 4 + ch].e[0];
+			u = u >= 255u ? u - 255u : u;
+		}
+		return (int) u - 127;
+	}
+	for (int i = 0; i < kTileThreads; ++i)
+		s_carry[i * 4 + ch] = 0;
+	return 0;
+}
+
+__device__ __forceinline__ RgbTables shfl_down_tables(const RgbTables &t, int delta)
+{
+	RgbTables o;
+#pragma unroll
+	for (int g = 0; g < 4; ++g) {
+		o.r[g] = __shfl_down_sync(0xFFFFFFFFu, t.r[g], delta);
+		o.b[g] = __shfl_down_sync(0xFFFFFFFFu, t.b[g], delta);
+	}
+	o.g[0] = __shfl_down_sync(0xFFFFFFFFu, t.g[0], delta);
+	o.g[1] = __shfl_down_sync(0xFFFFFFFFu, t.g[1], delta);
+	return o;
+}
+
+// the tables of a run as the three ByteMaps the scan and apply kernels read (little-endian words = table bytes)
+__device__ __forceinline__ void store_rgb_maps(const RgbTables &t, ByteMap *dst /* [>= 3] */)
+{
+	uint4 *d = reinterpret_cast<uint4 *>(dst);
+	const uint4 z = make_uint4(0, 0, 0, 0);
+	d[0] = make_uint4(t.r[0], t.r[1], t.r[2], t.r[3]);
+	d[1] = z;
+	d[2] = make_uint4(t.g[0], t.g[1], 0, 0);
+	d[3] = z;
+	d[4] = make_uint4(t.b[0], t.b[1], t.b[2], t.b[3]);
+	d[5] = z;
+}
+
 __global__ void __launch_bounds__(kTileThreads)
 dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kinds, size_t npixels,
 		const DitherLut *__restrict__ lut, ByteMap *__restrict__ chunkmaps /* [chunks][4] */,
@@ -61,7 +121,7 @@ dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kind
 {
 	__shared__ __align__(16) uint32_t s_lut3[256][4];
 	__shared__ uint32_t s_lut2[256];
-	__shared__ ByteMap s_maps[kTileThreads][4];
+	__shared__ ByteMap s_amap[kTileThreads]; // DXT3 alpha maps only
 	const int t = threadIdx.x;
 	for (int i = t; i < 256 * 4; i += kTileThreads)
 		(&s_lut3[0][0])[i] = (&lut->lut3[0][0])[i];
@@ -110,37 +170,74 @@ dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kind
 					s_lut3, s_lut2);
 		}
 	}
-	ByteMap m[4];
-	rgb_tables_store(tab, m[0], m[1], m[2]);
+	// ---- chunk maps out; tile map = composition of the 128 chunk maps --------------------------------------------
+	// Colour channels: the tables stay in registers; 5 shuffle levels inside a warp (a join is ~60 byte permutes, no
+	// memory), then the four warp results meet in shared memory.  The first version composed byte by byte in shared
+	// memory through 7 barrier levels, a third of this kernel's time (profiles/r01h).
+	const size_t chunk = (size_t) blockIdx.x * kTileThreads + t;
+	const int lane = t & 31, warp = t >> 5;
+	store_rgb_maps(tab, chunkmaps + chunk * 4);
+	ByteMap ma; // alpha: explicit 31-state map (DXT3), or the sum of sources mod 255 in e[0] (diffuse1), or nothing
 	if (kinds.k[3] == kChanShift4)
-		alpha_map_of_run(m[3], kChanShift4, src + first * 4 + 3, 4, count); // DXT3 only: 31 explicit trajectories
+		alpha_map_of_run(ma, kChanShift4, src + first * 4 + 3, 4, count); // DXT3 only: 31 explicit trajectories
 	else {
 #pragma unroll
 		for (int k = 0; k < 32; ++k)
-			m[3].e[k] = 0;
-		m[3].e[0] = (uint8_t) (asum % 255u); // diffuse1: the carry is a running sum mod 255
+			ma.e[k] = 0;
+		ma.e[0] = (uint8_t) (asum % 255u);
 	}
-	const size_t chunk = (size_t) blockIdx.x * kTileThreads + t;
+	chunkmaps[chunk * 4 + 3] = ma;
+
 #pragma unroll
-	for (int ch = 0; ch < 4; ++ch) {
-		chunkmaps[chunk * 4 + ch] = m[ch];
-		s_maps[t][ch] = m[ch];
+	for (int delta = 1; delta < 32; delta <<= 1) {
+		const RgbTables right = shfl_down_tables(tab, delta);
+		RgbTables both;
+		rgb_tables_join(both, tab, right); // mine first, then the run to my right
+		tab = both;                        // meaningful in lanes that are multiples of 2 * delta
+		asum += __shfl_down_sync(0xFFFFFFFFu, asum, delta);
 	}
-	__syncthreads();
-	// tree reduction: s_maps[t] <- s_maps[t] then s_maps[t + stride]
-	for (int stride = 1; stride < kTileThreads; stride <<= 1) {
-		if ((t & (2 * stride - 1)) == 0) {
-#pragma unroll
-			for (int ch = 0; ch < 4; ++ch) {
-				ByteMap r;
-				bmap_compose(r, s_maps[t][ch], s_maps[t + stride][ch], kinds.k[ch]);
-				s_maps[t][ch] = r;
-			}
-		}
+	__shared__ RgbTables s_warp[kTileThreads / 32];
+	__shared__ uint32_t s_asum[kTileThreads / 32];
+	if (lane == 0) {
+		s_warp[warp] = tab;
+		s_asum[warp] = asum;
+	}
+	if (kinds.k[3] == kChanShift4) { // byte-wise tree for the 31-state alpha maps only
+		s_amap[t] = ma;
 		__syncthreads();
+		for (int stride = 1; stride < kTileThreads; stride <<= 1) {
+			if ((t & (2 * stride - 1)) == 0) {
+				ByteMap r;
+				bmap_compose(r, s_amap[t], s_amap[t + stride], kChanShift4);
+				s_amap[t] = r;
+			}
+			__syncthreads();
+		}
+	} else
+		__syncthreads();
+	if (t == 0) {
+		RgbTables acc = s_warp[0];
+		uint32_t sum = s_asum[0];
+#pragma unroll
+		for (int w = 1; w < kTileThreads / 32; ++w) {
+			RgbTables both;
+			rgb_tables_join(both, acc, s_warp[w]);
+			acc = both;
+			sum += s_asum[w];
+		}
+		ByteMap *tm = tilemaps + (size_t) blockIdx.x * 4;
+		store_rgb_maps(acc, tm);
+		if (kinds.k[3] == kChanShift4)
+			tm[3] = s_amap[0];
+		else {
+			ByteMap m3;
+#pragma unroll
+			for (int k = 0; k < 32; ++k)
+				m3.e[k] = 0;
+			m3.e[0] = (uint8_t) (sum % 255u);
+			tm[3] = m3;
+		}
 	}
-	if (t < 4)
-		tilemaps[(size_t) blockIdx.x * 4 + t] = s_maps[0][t];
 }
 
 // One CTA of 32 warps.  A warp holds a map with entry k in lane k, so composing two maps is ONE shuffle
@@ -278,7 +375,10 @@ dither_scan_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKind
 	}
 }
 
-__global__ void __launch_bounds__(kTileThreads)
+#ifndef S2TC_APPLY_MINBLOCKS
+#define S2TC_APPLY_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(kTileThreads, S2TC_APPLY_MINBLOCKS)
 dither_apply_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits, ChanKinds kinds, size_t npixels,
 		const ByteMap *__restrict__ chunkmaps, const int *__restrict__ tile_carry, uint32_t *__restrict__ out)
 {
@@ -292,37 +392,39 @@ dither_apply_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits
 			s[i] = __ldg(g + i);
 	}
 	__syncthreads();
-	if (t < 4) { // one lane per channel walks the 128 chunk maps of the tile
-		int c = tile_carry[(size_t) blockIdx.x * 4 + t];
-		const int kind = kinds.k[t];
-		for (int i = 0; i < kTileThreads; ++i) {
-			s_carry[i * 4 + t] = c;
-			c = bmap_apply(s_maps[i * 4 + t], kind, c);
-		}
+	const size_t first = ((size_t) blockIdx.x * kTileThreads + t) * kChunk;
+	const int count = first >= npixels ? 0 : (int) min((size_t) kChunk, npixels - first);
+	const bool vec = srccomps == 4 && count == kChunk && (((size_t) src | (size_t) out) & 15) == 0;
+	const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(src) + first);
+	uint4 q[8];
+	if (vec) { // the first 128 bytes of the chunk are on their way while the carries are walked
+#pragma unroll
+		for (int j = 0; j < 8; ++j)
+			q[j] = __ldg(p + j);
+	}
+	if ((t & 31) == 0) { // one lane of each warp walks one channel through the 128 chunk maps of the tile
+		const int ch = t >> 5;
+		walk_chunk_carries(s_maps, s_carry, ch, kinds.k[ch], tile_carry[(size_t) blockIdx.x * 4 + ch]);
 	}
 	__syncthreads();
 
-	const size_t first = ((size_t) blockIdx.x * kTileThreads + t) * kChunk;
-	const int count = first >= npixels ? 0 : (int) min((size_t) kChunk, npixels - first);
 	int carry[4] = {s_carry[t * 4 + 0], s_carry[t * 4 + 1], s_carry[t * 4 + 2], s_carry[t * 4 + 3]};
 	const bool has_alpha = srccomps == 4;
 	const int ak = kinds.k[3];
-	if (srccomps == 4 && count == kChunk && (((size_t) src | (size_t) out) & 15) == 0) {
+	if (vec) {
 		// each thread streams its own 512 contiguous bytes: 8 x 128-bit loads in flight, replay, 128-bit stores
-		const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(src) + first);
 		uint4 *o = reinterpret_cast<uint4 *>(out + first);
 		for (int i = 0; i < kChunk / 4; i += 8) {
-			uint4 q[8];
-#pragma unroll
-			for (int j = 0; j < 8; ++j)
-				q[j] = __ldg(p + i + j);
 #pragma unroll
 			for (int j = 0; j < 8; ++j) {
-				q[j].x = replay_texel(carry, q[j].x, ak, true, alphabits);
-				q[j].y = replay_texel(carry, q[j].y, ak, true, alphabits);
-				q[j].z = replay_texel(carry, q[j].z, ak, true, alphabits);
-				q[j].w = replay_texel(carry, q[j].w, ak, true, alphabits);
-				o[i + j] = q[j];
+				uint4 v = q[j];
+				if (i + 8 < kChunk / 4)
+					q[j] = __ldg(p + i + 8 + j); // next batch
+				v.x = replay_texel(carry, v.x, ak, true, alphabits);
+				v.y = replay_texel(carry, v.y, ak, true, alphabits);
+				v.z = replay_texel(carry, v.z, ak, true, alphabits);
+				v.w = replay_texel(carry, v.w, ak, true, alphabits);
+				o[i + j] = v;
 			}
 		}
 	} else {
@@ -331,8 +433,8 @@ dither_apply_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits
 			if (srccomps == 4)
 				w = __ldg(reinterpret_cast<const uint32_t *>(src) + first + i);
 			else {
-				const uint8_t *q = src + (first + i) * 3;
-				w = (uint32_t) __ldg(q) | ((uint32_t) __ldg(q + 1) << 8) | ((uint32_t) __ldg(q + 2) << 16);
+				const uint8_t *qq = src + (first + i) * 3;
+				w = (uint32_t) __ldg(qq) | ((uint32_t) __ldg(qq + 1) << 8) | ((uint32_t) __ldg(qq + 2) << 16);
 			}
 			out[first + i] = replay_texel(carry, w, ak, has_alpha, alphabits);
 		}
@@ -388,14 +490,9 @@ dither_small_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits
 			s_maps[t * 4 + ch] = m[ch];
 	}
 	__syncthreads();
-	if (t < 4) {
-		int c = carry[t];
-		const int kind = kinds.k[t];
-		for (int i = 0; i < kTileThreads; ++i) {
-			s_carry[i * 4 + t] = c;
-			c = bmap_apply(s_maps[i * 4 + t], kind, c);
-		}
-		carry[t] = c;
+	if ((t & 31) == 0) {
+		const int ch = t >> 5;
+		carry[ch] = walk_chunk_carries(s_maps, s_carry, ch, kinds.k[ch], carry[ch]);
 	}
 	__syncthreads();
 	int cc[4] = {s_carry[t * 4 + 0], s_carry[t * 4 + 1], s_carry[t * 4 + 2], s_carry[t * 4 + 3]};
