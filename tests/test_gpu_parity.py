@@ -81,6 +81,26 @@ def test_srgb_negative_sums(encoder):
         _cmp(encoder, img, dxt, O.SRGB, nr, rf, O.DITHER_NONE, cursor=2)
 
 
+def test_search_tile_shapes(encoder):
+    """pair_search walks the pair triangle in 16x16 tiles, tile columns two at a time plus the diagonal tiles: cover
+    1 to 8 tile columns (odd and even), rows beyond m in the last tile, both row widths (16-bit: WAVG and alpha;
+    32-bit: RGB, SRGB_MIXED) and blocks with fewer than 16 colours (DXT1 transparency)."""
+    img = synth.synth_rgba(96, 64, seed=21)
+    for nr in (1, 13, 15, 17, 31, 33, 48, 64, 65, 100, 112):
+        for dxt, cd in ((O.DXT1, O.WAVG), (O.DXT5, O.WAVG), (O.DXT5, O.RGB), (O.DXT3, O.SRGB_MIXED)):
+            _cmp(encoder, img, dxt, cd, nr, O.LOOP, O.DITHER_NONE, cursor=3)
+
+
+def test_search16_full_and_partial_warps(encoder):
+    """search16 takes its fast path only when all 32 blocks of a warp have 16 candidates: an opaque image (every warp
+    full), the synthetic alpha patches (DXT1: mixed warps) and a ragged image (edge blocks), all eight metrics."""
+    opaque = synth.synth_rgba(256, 64, seed=22)
+    opaque[..., 3] = 255
+    for img in (opaque, synth.synth_rgba(256, 64, seed=23), synth.synth_noise(130, 35, seed=24)):
+        for dxt, cd, rf in itertools.product((O.DXT1, O.DXT3, O.DXT5), range(8), (O.NEVER, O.LOOP)):
+            _cmp(encoder, img, dxt, cd, 0, rf, O.DITHER_SIMPLE)
+
+
 def test_rand_cursor_continuity(encoder):
     """Two consecutive calls continue one rand() stream (mip levels, successive textures)."""
     a = synth.synth_rgba(32, 32, seed=1)
