@@ -182,9 +182,11 @@ int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &
 		RandPlan *dp = (RandPlan *) c->plans.p + c->plan_next;
 		c->plan_next++;
 		rand_plan_init(*hp, cursor0 + (uint64_t) blk0 * dpb, (uint64_t) kBlocksPerRandThread * dpb);
-		CU(cudaMemcpyAsync(dp, hp, sizeof(RandPlan), cudaMemcpyHostToDevice, st));
+		const RandPlan *hp_dev = nullptr;
+		CU(cudaHostGetDevicePointer((void **) &hp_dev, hp, 0));
+		CU(launch_plan_upload(hp_dev, dp, st));
 		CU(c->rand_ws.reserve(random_candidates_workspace_bytes((size_t) nblocks, kBlocksPerRandThread)));
-		FamScope f(c, st, kFamCand, 2);
+		FamScope f(c, st, kFamCand, 3);
 		CU(launch_random_candidates(s.dxt, nrandom, v, dp, kBlocksPerRandThread, (uint32_t *) c->rand_ws.p, (uint16_t *) c->cand_c.p,
 				(uint8_t *) c->cand_a.p, st));
 	}
@@ -310,7 +312,7 @@ int s2tc_b200_ctx_create(int device, s2tc_b200_ctx **out)
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
 	CU(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
-	CU(cudaHostAlloc((void **) &c->h_plans, sizeof(RandPlan) * kPlanRing, cudaHostAllocDefault));
+	CU(cudaHostAlloc((void **) &c->h_plans, sizeof(RandPlan) * kPlanRing, cudaHostAllocMapped));
 	CU(cudaHostAlloc((void **) &c->h_carry, 4 * sizeof(int), cudaHostAllocDefault));
 	CU(cudaHostAlloc((void **) &c->h_summary, 16 * sizeof(uint64_t), cudaHostAllocDefault));
 	CU(cudaHostAlloc((void **) &c->h_block, 128, cudaHostAllocDefault));
@@ -515,7 +517,10 @@ int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int
 	// instead of their sum.  The two pieces of cross-slab state stay on the device: the DITHER_SIMPLE carry
 	// (chained through d_carry on the compute stream) and the rand cursor (closed form per block row).
 	static const int slab_mb = [] { const char *e = getenv("S2TC_B200_SLAB_MB"); int n = e ? atoi(e) : 0; return n > 0 ? n : 16; }();
-	int nslab = (int) (in_bytes / ((size_t) slab_mb << 20)); // ~16 MiB of texels per slab by default (measured on config 2: 32 / 16 / 8 MiB -> e2e 5.9 / 5.5 / 7.2 ms)
+	// ~16 MiB of texels per slab by default (measured on config 2: 32 / 16 / 8 MiB -> e2e 5.9 / 5.5 / 7.2 ms); with random
+	// candidates the kernels dominate the copies and every slab costs a jump-ahead plan on the host and a candidate
+	// launch that small slabs cannot fill: 4x larger slabs
+	int nslab = (int) (in_bytes / ((size_t) slab_mb << (s.nrandom > 0 ? 22 : 20)));
 	nslab = nslab < 1 ? 1 : (nslab > 64 ? 64 : nslab);
 	if (nslab > bh)
 		nslab = bh;
@@ -526,10 +531,24 @@ int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int
 		d_carry = (int *) c->small.p + 8;
 		CU(cudaMemsetAsync(d_carry, 0, 4 * sizeof(int), st));
 	}
-	std::vector<cudaEvent_t> up(nslab), done(nslab);
+	// S2TC_B200_TRACE=1: print when every slab's upload, kernels and download finished (ms since the call started)
+	static const bool trace = getenv("S2TC_B200_TRACE") && atoi(getenv("S2TC_B200_TRACE"));
+	const unsigned evflags = trace ? cudaEventDefault : cudaEventDisableTiming;
+	std::vector<cudaEvent_t> up(nslab), done(nslab), down(trace ? nslab : 0);
+	cudaEvent_t t0 = nullptr;
 	for (int i = 0; i < nslab; ++i) {
-		CU(cudaEventCreateWithFlags(&up[i], cudaEventDisableTiming));
-		CU(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&up[i], evflags));
+		CU(cudaEventCreateWithFlags(&done[i], evflags));
+		if (trace)
+			CU(cudaEventCreate(&down[i]));
+	}
+	if (trace) {
+		CU(cudaEventCreate(&t0));
+		CU(cudaEventRecord(t0, st));
+		if (nslab > 1) {
+			CU(cudaStreamWaitEvent(c->copy_in, t0, 0));
+			CU(cudaStreamWaitEvent(c->copy_out, t0, 0));
+		}
 	}
 	int rc = 0;
 	for (int i = 0; i < nslab && !rc; ++i) {
@@ -538,7 +557,7 @@ int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int
 		const size_t off = (size_t) y0 * width * comps, len = (size_t) (y1 - y0) * width * comps;
 		cudaStream_t sin_ = nslab > 1 ? c->copy_in : st, sout = nslab > 1 ? c->copy_out : st;
 		CU(cudaMemcpyAsync((uint8_t *) c->src.p + off, src + off, len, cudaMemcpyHostToDevice, sin_));
-		if (nslab > 1) {
+		if (nslab > 1 || trace) {
 			CU(cudaEventRecord(up[i], sin_));
 			CU(cudaStreamWaitEvent(st, up[i], 0));
 		}
@@ -546,7 +565,7 @@ int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int
 		rc = encode_rows(c, s, comps, width, height, (const uint8_t *) c->src.p + off, r0, r1, d_out, cursor, d_carry, st);
 		if (rc)
 			break;
-		if (nslab > 1) {
+		if (nslab > 1 || trace) {
 			CU(cudaEventRecord(done[i], st));
 			CU(cudaStreamWaitEvent(sout, done[i], 0));
 		}
@@ -554,16 +573,31 @@ int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int
 			CU(cudaMemcpyAsync(dest + (size_t) r0 * tight, d_out, (size_t) (r1 - r0) * tight, cudaMemcpyDeviceToHost, sout));
 		else if (row_bytes > tight)
 			CU(cudaMemcpy2DAsync(dest + (size_t) r0 * row_bytes, row_bytes, d_out, tight, tight, r1 - r0, cudaMemcpyDeviceToHost, sout));
+		if (trace)
+			CU(cudaEventRecord(down[i], sout));
 	}
 	cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaSuccess, e3 = cudaSuccess;
 	if (nslab > 1) {
 		e2 = cudaStreamSynchronize(c->copy_in);
 		e3 = cudaStreamSynchronize(c->copy_out);
 	}
+	if (trace && !rc) {
+		for (int i = 0; i < nslab; ++i) {
+			float a = 0, b = 0, d = 0;
+			cudaEventElapsedTime(&a, t0, up[i]);
+			cudaEventElapsedTime(&b, t0, done[i]);
+			cudaEventElapsedTime(&d, t0, down[i]);
+			fprintf(stderr, "s2tc_b200 trace: slab %2d/%d  uploaded %8.3f  encoded %8.3f  downloaded %8.3f ms\n", i, nslab, a, b, d);
+		}
+	}
 	for (int i = 0; i < nslab; ++i) {
 		cudaEventDestroy(up[i]);
 		cudaEventDestroy(done[i]);
+		if (trace)
+			cudaEventDestroy(down[i]);
 	}
+	if (t0)
+		cudaEventDestroy(t0);
 	if (rc)
 		return rc;
 	CU(e1);

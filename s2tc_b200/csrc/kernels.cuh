@@ -105,6 +105,8 @@ cudaError_t launch_fast_encode(int dxt, int cd, int refine, const ImageView &v, 
 // d_cand_c: [blocks][nrandom] uint16 (565), d_cand_a: [blocks][nrandom] uint8 (DXT5 only)
 // d_windows: workspace of random_candidates_workspace_bytes(blocks, blocks_per_thread)
 size_t random_candidates_workspace_bytes(size_t nblocks, int blocks_per_thread);
+// plan: mapped pinned host memory -> device memory, by a kernel (no DMA engine involved)
+cudaError_t launch_plan_upload(const RandPlan *mapped_host_plan, RandPlan *d_plan, cudaStream_t stream);
 cudaError_t launch_random_candidates(int dxt, int nrandom, const ImageView &v, const RandPlan *d_plan,
 		int blocks_per_thread, uint32_t *d_windows, uint16_t *d_cand_c, uint8_t *d_cand_a, cudaStream_t stream);
 
