@@ -117,11 +117,15 @@ S2TC_HD void bmap_compose(ByteMap &out, const ByteMap &first, const ByteMap &sec
 }
 
 // ---- byte permute -----------------------------------------------------------------------------------
-// out byte i = byte (s >> 4i) & 7 of the 8-byte table {y:x}; selectors here never set bit 3
+// out byte i = byte (s >> 4i) & 7 of the 8-byte table {y:x}.  Selectors here never set bit 3 of a nibble, and only
+// the low 16 bits of s count, which is exactly PRMT's contract: raw prmt.b32 instead of __byte_perm, which ANDs every
+// selector with 0x7777 first (17 LOP3 per texel in the maps kernel, profiles/r01h).
 S2TC_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s)
 {
 #if defined(__CUDA_ARCH__)
-	return __byte_perm(x, y, s);
+	uint32_t d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(y), "r"(s));
+	return d;
 #else
 	const uint64_t t = ((uint64_t) y << 32) | x;
 	uint32_t r = 0;
@@ -183,8 +187,19 @@ S2TC_HD void rgb_tables_init(RgbTables &t)
 	t.r[3] = t.b[3] = 0x0F0E0D0Cu;
 }
 
+// x >> 16 as a multiply-high by k16 = 65536.  The kernels pass k16 as an argument the compiler cannot fold, so the
+// nine selector shifts per texel run on the FMA pipe (IMAD.HI) instead of the ALU pipe, which bounds the maps kernel.
+S2TC_HD uint32_t upper_half(uint32_t x, uint32_t k16)
+{
+#if defined(__CUDA_ARCH__)
+	return __umulhi(x, k16);
+#else
+	return (uint32_t) (((uint64_t) x * k16) >> 32);
+#endif
+}
+
 // A <- A o M(v) for a 16-byte table; L = the four words of lut3[v]
-S2TC_HD void table16_step(uint32_t (&T)[4], uint32_t l0, uint32_t l1, uint32_t l2, uint32_t l3)
+S2TC_HD void table16_step(uint32_t (&T)[4], uint32_t l0, uint32_t l1, uint32_t l2, uint32_t l3, uint32_t k16)
 {
 	const uint32_t L[4] = {l0, l1, l2, l3};
 	uint32_t n[4];
@@ -192,7 +207,7 @@ S2TC_HD void table16_step(uint32_t (&T)[4], uint32_t l0, uint32_t l1, uint32_t l
 	for (int g = 0; g < 4; ++g) {
 		const uint32_t lo = byte_perm(T[0], T[1], L[g]);
 		const uint32_t hi = byte_perm(T[2], T[3], L[g]);
-		n[g] = byte_perm(lo, hi, L[g] >> 16);
+		n[g] = byte_perm(lo, hi, upper_half(L[g], k16));
 	}
 #pragma unroll
 	for (int g = 0; g < 4; ++g)
@@ -200,13 +215,13 @@ S2TC_HD void table16_step(uint32_t (&T)[4], uint32_t l0, uint32_t l1, uint32_t l
 }
 
 // prepend one texel (w = raw r | g << 8 | b << 16 | ...) to the run summarised by t
-S2TC_HD void rgb_tables_prepend(RgbTables &t, uint32_t w, const uint32_t (*lut3)[4], const uint32_t *lut2)
+S2TC_HD void rgb_tables_prepend(RgbTables &t, uint32_t w, const uint32_t (*lut3)[4], const uint32_t *lut2, uint32_t k16 = 65536u)
 {
 	const uint32_t *lr = lut3[w & 0xFFu], *lb = lut3[(w >> 16) & 0xFFu];
-	table16_step(t.r, lr[0], lr[1], lr[2], lr[3]);
-	table16_step(t.b, lb[0], lb[1], lb[2], lb[3]);
+	table16_step(t.r, lr[0], lr[1], lr[2], lr[3], k16);
+	table16_step(t.b, lb[0], lb[1], lb[2], lb[3], k16);
 	const uint32_t s = lut2[(w >> 8) & 0xFFu];
-	const uint32_t g0 = byte_perm(t.g[0], t.g[1], s), g1 = byte_perm(t.g[0], t.g[1], s >> 16);
+	const uint32_t g0 = byte_perm(t.g[0], t.g[1], s), g1 = byte_perm(t.g[0], t.g[1], upper_half(s, k16));
 	t.g[0] = g0;
 	t.g[1] = g1;
 }

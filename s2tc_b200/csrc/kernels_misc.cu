@@ -56,6 +56,28 @@ constexpr int kTilePixels = kChunk * kTileThreads;
 
 static_assert(kTileThreads == 128, "one warp per channel walks the chunk carries");
 
+// 5 KB of selectors, global -> shared: 128-bit loads, all of a thread's loads in flight together (as a word loop this
+// prologue was a quarter of the maps kernel's stall samples: ten dependent round trips per CTA)
+__device__ __forceinline__ void load_dither_lut(const DitherLut *__restrict__ lut, uint32_t (*s_lut3)[4], uint32_t *s_lut2, int t)
+{
+	static_assert(sizeof(DitherLut) == (256 * 4 + 256) * 4, "lut3 then lut2, contiguous");
+	const uint4 *g = reinterpret_cast<const uint4 *>(lut);
+	uint4 v[3];
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const int i = t + k * kTileThreads;
+		v[k] = i < 320 ? __ldg(g + i) : make_uint4(0, 0, 0, 0);
+	}
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const int i = t + k * kTileThreads;
+		if (i < 256)
+			reinterpret_cast<uint4 *>(s_lut3)[i] = v[k];
+		else if (i < 320)
+			reinterpret_cast<uint4 *>(s_lut2)[i - 256] = v[k];
+	}
+}
+
 // Walks one channel through the tile's 128 chunk maps: s_carry[i * 4 + ch] = carry entering chunk i; returns the carry
 // after the last chunk.  Called by ONE lane per channel, each in a different warp: the kinds are different code
 // paths, and a warp that ran them in four of its lanes serialised them (the walk was a third of the apply kernel's
@@ -88,16 +110,16 @@ __device__ __forceinline__ int walk_chunk_carries(const ByteMap *s_maps, int *s_
 	return 0;
 }
 
-__device__ __forceinline__ RgbTables shfl_down_tables(const RgbTables &t, int delta)
+__device__ __forceinline__ RgbTables shfl_up_tables(const RgbTables &t, int delta)
 {
 	RgbTables o;
 #pragma unroll
 	for (int g = 0; g < 4; ++g) {
-		o.r[g] = __shfl_down_sync(0xFFFFFFFFu, t.r[g], delta);
-		o.b[g] = __shfl_down_sync(0xFFFFFFFFu, t.b[g], delta);
+		o.r[g] = __shfl_up_sync(0xFFFFFFFFu, t.r[g], delta);
+		o.b[g] = __shfl_up_sync(0xFFFFFFFFu, t.b[g], delta);
 	}
-	o.g[0] = __shfl_down_sync(0xFFFFFFFFu, t.g[0], delta);
-	o.g[1] = __shfl_down_sync(0xFFFFFFFFu, t.g[1], delta);
+	o.g[0] = __shfl_up_sync(0xFFFFFFFFu, t.g[0], delta);
+	o.g[1] = __shfl_up_sync(0xFFFFFFFFu, t.g[1], delta);
 	return o;
 }
 
@@ -114,19 +136,19 @@ __device__ __forceinline__ void store_rgb_maps(const RgbTables &t, ByteMap *dst 
 	d[5] = z;
 }
 
-__global__ void __launch_bounds__(kTileThreads)
+#ifndef S2TC_MAPS_MINBLOCKS
+#define S2TC_MAPS_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(kTileThreads, S2TC_MAPS_MINBLOCKS)
 dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kinds, size_t npixels,
-		const DitherLut *__restrict__ lut, ByteMap *__restrict__ chunkmaps /* [chunks][4] */,
-		ByteMap *__restrict__ tilemaps /* [tiles][4] */)
+		const DitherLut *__restrict__ lut, uint32_t k16 /* 65536, opaque: see upper_half */,
+		ByteMap *__restrict__ chunkmaps /* [chunks][4] */, ByteMap *__restrict__ tilemaps /* [tiles][4] */)
 {
 	__shared__ __align__(16) uint32_t s_lut3[256][4];
-	__shared__ uint32_t s_lut2[256];
+	__shared__ __align__(16) uint32_t s_lut2[256];
 	__shared__ ByteMap s_amap[kTileThreads]; // DXT3 alpha maps only
 	const int t = threadIdx.x;
-	for (int i = t; i < 256 * 4; i += kTileThreads)
-		(&s_lut3[0][0])[i] = (&lut->lut3[0][0])[i];
-	for (int i = t; i < 256; i += kTileThreads)
-		s_lut2[i] = lut->lut2[i];
+	load_dither_lut(lut, s_lut3, s_lut2, t);
 	__syncthreads();
 
 	const size_t first = ((size_t) blockIdx.x * kTileThreads + t) * kChunk;
@@ -142,14 +164,14 @@ dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kind
 #pragma unroll 2
 		for (int i = kChunk / 8 - 1; i >= 0; --i) { // right to left, four texels per 128-bit load
 			const uint4 ql = __ldg(p + i), qr = __ldg(p + kChunk / 8 + i);
-			rgb_tables_prepend(left, ql.w, s_lut3, s_lut2);
-			rgb_tables_prepend(tab, qr.w, s_lut3, s_lut2);
-			rgb_tables_prepend(left, ql.z, s_lut3, s_lut2);
-			rgb_tables_prepend(tab, qr.z, s_lut3, s_lut2);
-			rgb_tables_prepend(left, ql.y, s_lut3, s_lut2);
-			rgb_tables_prepend(tab, qr.y, s_lut3, s_lut2);
-			rgb_tables_prepend(left, ql.x, s_lut3, s_lut2);
-			rgb_tables_prepend(tab, qr.x, s_lut3, s_lut2);
+			rgb_tables_prepend(left, ql.w, s_lut3, s_lut2, k16);
+			rgb_tables_prepend(tab, qr.w, s_lut3, s_lut2, k16);
+			rgb_tables_prepend(left, ql.z, s_lut3, s_lut2, k16);
+			rgb_tables_prepend(tab, qr.z, s_lut3, s_lut2, k16);
+			rgb_tables_prepend(left, ql.y, s_lut3, s_lut2, k16);
+			rgb_tables_prepend(tab, qr.y, s_lut3, s_lut2, k16);
+			rgb_tables_prepend(left, ql.x, s_lut3, s_lut2, k16);
+			rgb_tables_prepend(tab, qr.x, s_lut3, s_lut2, k16);
 			asum += (ql.x >> 24) + (ql.y >> 24) + (ql.z >> 24) + (ql.w >> 24) + (qr.x >> 24) + (qr.y >> 24) + (qr.z >> 24) + (qr.w >> 24);
 		}
 		RgbTables whole;
@@ -159,7 +181,7 @@ dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kind
 		const uint32_t *p = reinterpret_cast<const uint32_t *>(src) + first;
 		for (int i = count; i > 0; --i) {
 			const uint32_t w = __ldg(p + i - 1);
-			rgb_tables_prepend(tab, w, s_lut3, s_lut2);
+			rgb_tables_prepend(tab, w, s_lut3, s_lut2, k16);
 			asum += w >> 24;
 		}
 	} else {
@@ -167,44 +189,71 @@ dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kind
 		for (int i = count; i > 0; --i) {
 			const uint8_t *q = p + (size_t) (i - 1) * 3;
 			rgb_tables_prepend(tab, (uint32_t) __ldg(q) | ((uint32_t) __ldg(q + 1) << 8) | ((uint32_t) __ldg(q + 2) << 16),
-					s_lut3, s_lut2);
+					s_lut3, s_lut2, k16);
 		}
 	}
-	// ---- chunk maps out; tile map = composition of the 128 chunk maps --------------------------------------------
-	// Colour channels: the tables stay in registers; 5 shuffle levels inside a warp (a join is ~60 byte permutes, no
-	// memory), then the four warp results meet in shared memory.  The first version composed byte by byte in shared
-	// memory through 7 barrier levels, a third of this kernel's time (profiles/r01h).
+	// ---- prefix maps out; tile map = composition of the 128 chunk maps ---------------------------------------------
+	// What the replay needs for chunk t is the carry entering it: the composition of chunks 0 .. t-1 of the tile applied
+	// to the tile's carry.  So the tile is scanned here: an inclusive scan over the warp's 32 chunk tables through
+	// shuffles (5 levels; a join is ~60 byte permutes, tables stay in registers), the four warp totals meet in shared
+	// memory, and every thread stores the EXCLUSIVE prefix of its chunk.  (First version: per-chunk maps were stored
+	// and the replay kernel walked all 128 of them serially per channel before it could start.)
 	const size_t chunk = (size_t) blockIdx.x * kTileThreads + t;
 	const int lane = t & 31, warp = t >> 5;
-	store_rgb_maps(tab, chunkmaps + chunk * 4);
-	ByteMap ma; // alpha: explicit 31-state map (DXT3), or the sum of sources mod 255 in e[0] (diffuse1), or nothing
-	if (kinds.k[3] == kChanShift4)
-		alpha_map_of_run(ma, kChanShift4, src + first * 4 + 3, 4, count); // DXT3 only: 31 explicit trajectories
-	else {
-#pragma unroll
-		for (int k = 0; k < 32; ++k)
-			ma.e[k] = 0;
-		ma.e[0] = (uint8_t) (asum % 255u);
-	}
-	chunkmaps[chunk * 4 + 3] = ma;
-
+	const uint32_t asum_own = asum;
 #pragma unroll
 	for (int delta = 1; delta < 32; delta <<= 1) {
-		const RgbTables right = shfl_down_tables(tab, delta);
+		const RgbTables before = shfl_up_tables(tab, delta);
+		const uint32_t asum_before = __shfl_up_sync(0xFFFFFFFFu, asum, delta);
 		RgbTables both;
-		rgb_tables_join(both, tab, right); // mine first, then the run to my right
-		tab = both;                        // meaningful in lanes that are multiples of 2 * delta
-		asum += __shfl_down_sync(0xFFFFFFFFu, asum, delta);
+		rgb_tables_join(both, before, tab); // the run to my left first, then mine
+		if (lane >= delta) {
+			tab = both;
+			asum += asum_before;
+		}
 	}
 	__shared__ RgbTables s_warp[kTileThreads / 32];
 	__shared__ uint32_t s_asum[kTileThreads / 32];
-	if (lane == 0) {
+	if (lane == 31) {
 		s_warp[warp] = tab;
 		s_asum[warp] = asum;
 	}
-	if (kinds.k[3] == kChanShift4) { // byte-wise tree for the 31-state alpha maps only
+	ByteMap ma; // alpha of THIS chunk: explicit 31-state map (DXT3) -- those the replay kernel still walks
+	if (kinds.k[3] == kChanShift4) {
+		alpha_map_of_run(ma, kChanShift4, src + first * 4 + 3, 4, count); // DXT3 only: 31 explicit trajectories
 		s_amap[t] = ma;
-		__syncthreads();
+	}
+	__syncthreads();
+	// exclusive prefix inside the warp, then the warps to the left in front of it
+	RgbTables excl = shfl_up_tables(tab, 1);
+	if (lane == 0)
+		rgb_tables_init(excl);
+	uint32_t asum_excl = asum - asum_own;
+	RgbTables left; // chunks of warps 0 .. warp-1
+	rgb_tables_init(left);
+	for (int w = 0; w < warp; ++w) {
+		RgbTables both;
+		rgb_tables_join(both, left, s_warp[w]);
+		left = both;
+		asum_excl += s_asum[w];
+	}
+	if (warp > 0) {
+		RgbTables both;
+		rgb_tables_join(both, left, excl);
+		excl = both;
+	}
+	store_rgb_maps(excl, chunkmaps + chunk * 4);
+	if (kinds.k[3] == kChanShift4)
+		chunkmaps[chunk * 4 + 3] = ma;
+	else {
+		ByteMap m3;
+#pragma unroll
+		for (int k = 0; k < 32; ++k)
+			m3.e[k] = 0;
+		m3.e[0] = (uint8_t) (asum_excl % 255u); // diffuse1: sum of the sources in front of this chunk, mod 255
+		chunkmaps[chunk * 4 + 3] = m3;
+	}
+	if (kinds.k[3] == kChanShift4) { // byte-wise tree for the 31-state alpha maps only
 		for (int stride = 1; stride < kTileThreads; stride <<= 1) {
 			if ((t & (2 * stride - 1)) == 0) {
 				ByteMap r;
@@ -213,20 +262,12 @@ dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kind
 			}
 			__syncthreads();
 		}
-	} else
-		__syncthreads();
-	if (t == 0) {
-		RgbTables acc = s_warp[0];
-		uint32_t sum = s_asum[0];
-#pragma unroll
-		for (int w = 1; w < kTileThreads / 32; ++w) {
-			RgbTables both;
-			rgb_tables_join(both, acc, s_warp[w]);
-			acc = both;
-			sum += s_asum[w];
-		}
+	}
+	if (t == kTileThreads - 1) { // this thread's inclusive prefix is the whole tile
+		RgbTables whole;
+		rgb_tables_join(whole, left, tab);
 		ByteMap *tm = tilemaps + (size_t) blockIdx.x * 4;
-		store_rgb_maps(acc, tm);
+		store_rgb_maps(whole, tm);
 		if (kinds.k[3] == kChanShift4)
 			tm[3] = s_amap[0];
 		else {
@@ -234,7 +275,7 @@ dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kind
 #pragma unroll
 			for (int k = 0; k < 32; ++k)
 				m3.e[k] = 0;
-			m3.e[0] = (uint8_t) (sum % 255u);
+			m3.e[0] = (uint8_t) ((asum_excl + asum_own) % 255u);
 			tm[3] = m3;
 		}
 	}
@@ -375,6 +416,7 @@ dither_scan_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKind
 	}
 }
 
+constexpr int kStagePitch = 36; // words per staging row: 32 texels + 4, so that rows 4 banks apart serve 128-bit accesses conflict-free
 #ifndef S2TC_APPLY_MINBLOCKS
 #define S2TC_APPLY_MINBLOCKS 6
 #endif
@@ -382,36 +424,89 @@ __global__ void __launch_bounds__(kTileThreads, S2TC_APPLY_MINBLOCKS)
 dither_apply_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits, ChanKinds kinds, size_t npixels,
 		const ByteMap *__restrict__ chunkmaps, const int *__restrict__ tile_carry, uint32_t *__restrict__ out)
 {
-	__shared__ ByteMap s_maps[kTileThreads * 4];
-	__shared__ int s_carry[kTileThreads * 4];
 	const int t = threadIdx.x;
-	{
-		const uint4 *g = reinterpret_cast<const uint4 *>(chunkmaps + (size_t) blockIdx.x * kTileThreads * 4);
-		uint4 *s = reinterpret_cast<uint4 *>(s_maps);
-		for (int i = t; i < kTileThreads * 4 * 2; i += kTileThreads)
-			s[i] = __ldg(g + i);
-	}
-	__syncthreads();
-	const size_t first = ((size_t) blockIdx.x * kTileThreads + t) * kChunk;
+	const size_t chunk = (size_t) blockIdx.x * kTileThreads + t;
+	const size_t first = chunk * kChunk;
 	const int count = first >= npixels ? 0 : (int) min((size_t) kChunk, npixels - first);
 	const bool vec = srccomps == 4 && count == kChunk && (((size_t) src | (size_t) out) & 15) == 0;
+	// Full warps move their texels through shared memory so that global accesses are coalesced: a thread's chunk is 512
+	// contiguous bytes, so thread-private 128-bit accesses touch 32 different lines per warp instruction.  Instead the
+	// warp copies one 128-byte quarter of each of its 32 chunks per step (8 instructions, 4 whole lines each) into a
+	// staging row per thread (36-word pitch: conflict-free both ways), replays in place and copies back.
+	const int lane = t & 31, warp = t >> 5;
+	const bool staged = __all_sync(0xFFFFFFFFu, vec);
+	__shared__ __align__(16) uint32_t s_stage[kTileThreads * kStagePitch];
+	uint32_t *ws = s_stage + warp * 32 * kStagePitch;
+	const size_t warp_chunk0 = (size_t) blockIdx.x * kTileThreads + warp * 32;
+	const uint4 *gin = reinterpret_cast<const uint4 *>(src) + warp_chunk0 * (kChunk / 4);
+	const int cl = lane >> 3, piece = lane & 7; // this lane moves piece `piece` of chunks cl, cl + 4, ..., cl + 28
 	const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(src) + first);
 	uint4 q[8];
-	if (vec) { // the first 128 bytes of the chunk are on their way while the carries are walked
+	if (staged) { // the first quarter is on its way while the carry is looked up
+#pragma unroll
+		for (int k = 0; k < 8; ++k)
+			q[k] = __ldg(gin + (size_t) (4 * k + cl) * (kChunk / 4) + piece);
+	} else if (vec) {
 #pragma unroll
 		for (int j = 0; j < 8; ++j)
 			q[j] = __ldg(p + j);
 	}
-	if ((t & 31) == 0) { // one lane of each warp walks one channel through the 128 chunk maps of the tile
-		const int ch = t >> 5;
-		walk_chunk_carries(s_maps, s_carry, ch, kinds.k[ch], tile_carry[(size_t) blockIdx.x * 4 + ch]);
-	}
-	__syncthreads();
-
-	int carry[4] = {s_carry[t * 4 + 0], s_carry[t * 4 + 1], s_carry[t * 4 + 2], s_carry[t * 4 + 3]};
-	const bool has_alpha = srccomps == 4;
+	// carry entering this chunk = the chunk's prefix map (composition of the tile's earlier chunks, left by the maps
+	// kernel) applied to the carry entering the tile (left by the scan kernel)
+	const int *tc = tile_carry + (size_t) blockIdx.x * 4;
+	const ByteMap *cm = chunkmaps + chunk * 4;
 	const int ak = kinds.k[3];
-	if (vec) {
+	int carry[4];
+	carry[0] = (int) cm[0].e[__ldg(tc + 0) + 7] - 7;
+	carry[1] = (int) cm[1].e[__ldg(tc + 1) + 3] - 3;
+	carry[2] = (int) cm[2].e[__ldg(tc + 2) + 7] - 7;
+	carry[3] = ak == kChanBit1 ? balanced255(__ldg(tc + 3) + (int) cm[3].e[0]) : 0;
+	if (ak == kChanShift4) { // DXT3 alpha: 31-state per-chunk maps, walked by one lane (uniform branch)
+		__shared__ ByteMap s_amap[kTileThreads];
+		__shared__ int s_acarry[kTileThreads];
+		s_amap[t] = cm[3];
+		__syncthreads();
+		if (t == 0) {
+			uint32_t idx = (uint32_t) (__ldg(tc + 3) + 15);
+			for (int i = 0; i < kTileThreads; ++i) {
+				s_acarry[i] = (int) idx - 15;
+				idx = s_amap[i].e[idx];
+			}
+		}
+		__syncthreads();
+		carry[3] = s_acarry[t];
+	}
+	const bool has_alpha = srccomps == 4;
+	if (staged) {
+		uint4 *gout = reinterpret_cast<uint4 *>(out) + warp_chunk0 * (kChunk / 4);
+		for (int quarter = 0; quarter < 4; ++quarter) {
+#pragma unroll
+			for (int k = 0; k < 8; ++k)
+				*reinterpret_cast<uint4 *>(ws + (4 * k + cl) * kStagePitch + piece * 4) = q[k];
+			__syncwarp();
+			if (quarter < 3) {
+#pragma unroll
+				for (int k = 0; k < 8; ++k)
+					q[k] = __ldg(gin + (size_t) (4 * k + cl) * (kChunk / 4) + (quarter + 1) * 8 + piece);
+			}
+			uint4 *mine = reinterpret_cast<uint4 *>(ws + lane * kStagePitch);
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				uint4 v = mine[j];
+				v.x = replay_texel(carry, v.x, ak, true, alphabits);
+				v.y = replay_texel(carry, v.y, ak, true, alphabits);
+				v.z = replay_texel(carry, v.z, ak, true, alphabits);
+				v.w = replay_texel(carry, v.w, ak, true, alphabits);
+				mine[j] = v;
+			}
+			__syncwarp();
+#pragma unroll
+			for (int k = 0; k < 8; ++k)
+				gout[(size_t) (4 * k + cl) * (kChunk / 4) + quarter * 8 + piece] =
+						*reinterpret_cast<const uint4 *>(ws + (4 * k + cl) * kStagePitch + piece * 4);
+			__syncwarp();
+		}
+	} else if (vec) {
 		// each thread streams its own 512 contiguous bytes: 8 x 128-bit loads in flight, replay, 128-bit stores
 		uint4 *o = reinterpret_cast<uint4 *>(out + first);
 		for (int i = 0; i < kChunk / 4; i += 8) {
@@ -449,14 +544,11 @@ dither_small_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits
 		const DitherLut *__restrict__ lut, int *carry /* 4 ints in/out */, uint32_t *__restrict__ out)
 {
 	__shared__ __align__(16) uint32_t s_lut3[256][4];
-	__shared__ uint32_t s_lut2[256];
+	__shared__ __align__(16) uint32_t s_lut2[256];
 	__shared__ ByteMap s_maps[kTileThreads * 4];
 	__shared__ int s_carry[kTileThreads * 4];
 	const int t = threadIdx.x;
-	for (int i = t; i < 256 * 4; i += kTileThreads)
-		(&s_lut3[0][0])[i] = (&lut->lut3[0][0])[i];
-	for (int i = t; i < 256; i += kTileThreads)
-		s_lut2[i] = lut->lut2[i];
+	load_dither_lut(lut, s_lut3, s_lut2, t);
 	__syncthreads();
 	const int first = t * kChunk;
 	const int count = first >= npixels ? 0 : min(kChunk, npixels - first);
@@ -552,7 +644,7 @@ static cudaError_t run_dither(int phases, const void *d_src, int srccomps, int a
 	}
 	if (phases & 1)
 		dither_maps_kernel<<<(unsigned) tiles, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, kinds, npixels, lut,
-				chunkmaps, tilemaps);
+				65536u, chunkmaps, tilemaps);
 	if (phases & 2)
 		dither_scan_kernel<<<1, kScanThreads, 0, stream>>>(tilemaps, tiles, kinds, d_carry, tile_carry, d_summary);
 	if (phases & 4)
