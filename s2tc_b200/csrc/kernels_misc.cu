@@ -161,9 +161,14 @@ dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kind
 		const uint4 *p = reinterpret_cast<const uint4 *>(reinterpret_cast<const uint32_t *>(src) + first);
 		RgbTables left;
 		rgb_tables_init(left);
+		uint4 nl = __ldg(p + kChunk / 8 - 1), nr = __ldg(p + kChunk / 4 - 1);
 #pragma unroll 2
-		for (int i = kChunk / 8 - 1; i >= 0; --i) { // right to left, four texels per 128-bit load
-			const uint4 ql = __ldg(p + i), qr = __ldg(p + kChunk / 8 + i);
+		for (int i = kChunk / 8 - 1; i >= 0; --i) { // right to left, four texels per 128-bit load, the next pair in flight
+			const uint4 ql = nl, qr = nr;
+			if (i > 0) {
+				nl = __ldg(p + i - 1);
+				nr = __ldg(p + kChunk / 8 + i - 1);
+			}
 			rgb_tables_prepend(left, ql.w, s_lut3, s_lut2, k16);
 			rgb_tables_prepend(tab, qr.w, s_lut3, s_lut2, k16);
 			rgb_tables_prepend(left, ql.z, s_lut3, s_lut2, k16);
