@@ -112,14 +112,14 @@ __device__ __forceinline__ void fill120(int (&D)[120], int n, F dist, std::integ
 // No masking anywhere, and two changes that take work off the ALU pipe, which bounds the scans (ncu: ALU pipe ~90 %
 // busy inside the scans with the FMA pipe idle):
 //  * the 16-term sums accumulate through IMAD (m * one + s, `one` an opaque kernel argument equal to 1) in
-//    S2TC_ENCODE16_CHAINS independent chains (measured on config 2: 1 / 2 / 4 / 7 chains -> 1.99 / 1.93 / 1.75 / 1.72 ms)
+//    S2TC_SEARCH16_CHAINS independent chains (measured on config 2: 1 / 2 / 4 / 7 chains -> 1.99 / 1.93 / 1.75 / 1.72 ms)
 //    instead of IADD3 only: a pair costs 20 ALU + 7 FMA-pipe instructions instead of 24 ALU;
 //  * distances that fit 16 bits (alpha always; AVG / WAVG / W0AVG colours) are stored as full rows of 16-bit halves,
 //    the DXT5 fixed points folded in (min(d[i][k], fix[k]) is stored, as in kernels_search.cu): a pair is
 //    8 VIMNMX.U16x2 + 8 IDP.2A, and since the sums stay below 2^20 the whole acceptance rule is one unsigned min over
 //    keys (sum << 7) | pair_number ("first minimum in scan order", ref :393-410).
-#ifndef S2TC_ENCODE16_CHAINS
-#define S2TC_ENCODE16_CHAINS 7 // independent accumulation chains per pair sum
+#ifndef S2TC_SEARCH16_CHAINS
+#define S2TC_SEARCH16_CHAINS 7 // independent accumulation chains per pair sum
 #endif
 template <int CD> struct Fits16 { static constexpr bool value = CD == kAVG || CD == kWAVG || CD == kW0AVG; };
 
@@ -149,13 +149,13 @@ __device__ __forceinline__ uint32_t mad_opaque(uint32_t a, uint32_t b, uint32_t 
 template <int I, int J, bool SKIP, int... T>
 __device__ __forceinline__ int pair_sum_full(const int (&D)[120], uint32_t one, std::integer_sequence<int, T...>)
 {
-	uint32_t s[S2TC_ENCODE16_CHAINS];
+	uint32_t s[S2TC_SEARCH16_CHAINS];
 	auto term = [&](auto tc) {
 		constexpr int t = decltype(tc)::value;
 		constexpr int k = kth_col<I, J, SKIP>(t);
 		const uint32_t m = (uint32_t) min(sym<I, k>(D), sym<J, k>(D));
-		constexpr int ch = t % S2TC_ENCODE16_CHAINS;
-		if constexpr (t < S2TC_ENCODE16_CHAINS)
+		constexpr int ch = t % S2TC_SEARCH16_CHAINS;
+		if constexpr (t < S2TC_SEARCH16_CHAINS)
 			s[ch] = m;
 		else
 			s[ch] = mad_opaque(m, one, s[ch]);
@@ -165,7 +165,7 @@ __device__ __forceinline__ int pair_sum_full(const int (&D)[120], uint32_t one, 
 	// the live ranges until the matrix spills (2.13 vs 1.72 ms on config 2)
 	uint32_t r = s[0];
 #pragma unroll
-	for (int q = 1; q < S2TC_ENCODE16_CHAINS; ++q)
+	for (int q = 1; q < S2TC_SEARCH16_CHAINS; ++q)
 		r += s[q];
 	return (int) r;
 }
@@ -393,8 +393,8 @@ __device__ __noinline__ void search_any(const Block &b, uint32_t usemask, uint32
 	}
 }
 
-#ifndef S2TC_ENCODE16_MINBLOCKS
-#define S2TC_ENCODE16_MINBLOCKS 3
+#ifndef S2TC_SEARCH16_MINBLOCKS
+#define S2TC_SEARCH16_MINBLOCKS 3
 #endif
 constexpr int kSearch16Threads = 128;
 // Writes the chosen endpoints of every block, {c0 | c1 << 16 as RGB565, a0 | a1 << 8}, the layout finish_kernel
@@ -402,7 +402,7 @@ constexpr int kSearch16Threads = 128;
 // DXT5 runs it twice, once per search (COLOR writes the first word, ALPHA the second): each launch walks ~100 KB /
 // ~65 KB of straight-line code instead of ~150 KB in one kernel.  The alpha launch does not depend on the metric.
 template <int DXT, int CD, bool COLOR, bool ALPHA>
-__global__ void __launch_bounds__(kSearch16Threads, S2TC_ENCODE16_MINBLOCKS) search16_kernel(ImageView v, uint32_t one, uint2 *__restrict__ ends)
+__global__ void __launch_bounds__(kSearch16Threads, S2TC_SEARCH16_MINBLOCKS) search16_kernel(ImageView v, uint32_t one, uint2 *__restrict__ ends)
 {
 	const int nblocks = v.blocks_w * v.blocks_h;
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -457,8 +457,8 @@ static cudaError_t launch_search16_dxt(int cd, const ImageView &v, uint2 *d_ends
 		return cudaSuccess;
 	const dim3 block(kSearch16Threads), grid((nblocks + kSearch16Threads - 1) / kSearch16Threads);
 	switch (cd) {
-#ifdef S2TC_ENCODE16_ONLY_CD // A/B builds of a single metric (see the Makefile's EXTRA)
-	case S2TC_ENCODE16_ONLY_CD: launch_search16_cd<DXT, S2TC_ENCODE16_ONLY_CD>(grid, block, v, d_ends, stream); break;
+#ifdef S2TC_SEARCH16_ONLY_CD // A/B builds of a single metric (see the Makefile's EXTRA)
+	case S2TC_SEARCH16_ONLY_CD: launch_search16_cd<DXT, S2TC_SEARCH16_ONLY_CD>(grid, block, v, d_ends, stream); break;
 #else
 	case kRGB: launch_search16_cd<DXT, kRGB>(grid, block, v, d_ends, stream); break;
 	case kYUV: launch_search16_cd<DXT, kYUV>(grid, block, v, d_ends, stream); break;
@@ -475,9 +475,9 @@ static cudaError_t launch_search16_dxt(int cd, const ImageView &v, uint2 *d_ends
 }
 
 // one translation unit per DXT mode (the fully unrolled scans are slow to compile)
-cudaError_t S2TC_ENCODE16_NAME(int cd, const ImageView &v, uint2 *d_ends, cudaStream_t stream)
+cudaError_t S2TC_SEARCH16_NAME(int cd, const ImageView &v, uint2 *d_ends, cudaStream_t stream)
 {
-	return launch_search16_dxt<S2TC_ENCODE16_DXT>(cd, v, d_ends, stream);
+	return launch_search16_dxt<S2TC_SEARCH16_DXT>(cd, v, d_ends, stream);
 }
 
 } // namespace s2tc
