@@ -333,7 +333,7 @@ def main():
     dom = max(fam, key=lambda k: fam[k][0])
     dom_ms, dom_n = fam[dom]
     if dom == "prepass":
-        dom_n //= 3   # the three phases of the carry scan are timed as one group
+        dom_n //= 5   # maps, three scan launches and the replay are timed as one group
     search_group = 2 if (nrandom <= 0 and st.dxt == 2) else 1   # search16 runs DXT5 as a colour launch + an alpha launch
     if dom == "search":
         dom_n //= search_group

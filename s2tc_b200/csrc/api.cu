@@ -231,7 +231,7 @@ int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int
 		// a summary call on exactly these texels (sharded encodes do one to exchange carries) left their maps behind
 		const bool ready = c->maps_src == d_src_rows && c->maps_npix == npix && c->maps_comps == comps && c->maps_abits == abits;
 		c->maps_src = nullptr;
-		FamScope f(c, st, kFamPrepass, ready ? 2 : 3);
+		FamScope f(c, st, kFamPrepass, prepass_simple_launches(npix, ready));
 		CU(launch_prepass_simple(d_src_rows, comps, abits, npix, c->reduced.p, carry, c->dither_ws.p, ready, st));
 		texels = (const uint8_t *) c->reduced.p;
 		fmt = kSrcReduced;
@@ -402,7 +402,7 @@ int s2tc_b200_dither_summary_async(s2tc_b200_ctx *c, int srccomps, int alphabits
 	const int y0 = row0 * 4, y1 = row1 * 4 < height ? row1 * 4 : height;
 	const size_t npix = (size_t) width * (y1 - y0);
 	CU(c->dither_ws.reserve(dither_workspace_bytes(npix)));
-	FamScope f(c, st, kFamPrepass, 2);
+	FamScope f(c, st, kFamPrepass, kDitherSummaryLaunches);
 	CU(launch_dither_summary(d_src_rows, comps, alphabits, npix, (ByteMap *) d_maps, c->dither_ws.p, st));
 	c->maps_src = d_src_rows;
 	c->maps_npix = npix;
@@ -467,7 +467,7 @@ int s2tc_b200_dither_summary_device(s2tc_b200_ctx *c, int srccomps, int alphabit
 	}
 	CU(c->dither_ws.reserve(dither_workspace_bytes(npix)));
 	{
-		FamScope f(c, st, kFamPrepass, 2);
+		FamScope f(c, st, kFamPrepass, kDitherSummaryLaunches);
 		CU(launch_dither_summary(d_src_rows, comps, alphabits, npix, d_sum, c->dither_ws.p, st));
 		c->maps_src = d_src_rows; // encode_rows on the same texels may reuse the maps (same stream order assumed)
 		c->maps_npix = npix;
@@ -734,7 +734,7 @@ int s2tc_b200_rgb565_host(s2tc_b200_ctx *c, uint8_t *out, const uint8_t *src, in
 		int *carry = (int *) c->small.p;
 		CU(cudaMemsetAsync(carry, 0, 4 * sizeof(int), st));
 		c->maps_src = nullptr;
-		FamScope f(c, st, kFamPrepass, 3);
+		FamScope f(c, st, kFamPrepass, prepass_simple_launches(npix, false));
 		CU(launch_prepass_simple(c->src.p, comps, abits, npix, c->reduced.p, carry, c->dither_ws.p, false, st));
 	}
 	CU(cudaMemcpyAsync(out, c->reduced.p, npix * 4, cudaMemcpyDeviceToHost, st));

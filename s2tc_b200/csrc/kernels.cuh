@@ -143,6 +143,8 @@ size_t dither_workspace_bytes(size_t npixels);
 // texels), so phase 1 is skipped.
 cudaError_t launch_prepass_simple(const void *d_src, int srccomps, int alphabits, size_t npixels, void *d_reduced,
 		int *d_carry, void *d_workspace, bool maps_ready, cudaStream_t stream);
+int prepass_simple_launches(size_t npixels, bool maps_ready); // kernel launches the call above makes
+constexpr int kDitherSummaryLaunches = 3;                     // maps + two scan launches
 // transfer maps only (for sharding a carry chain across GPUs): d_summary receives 4 ByteMaps
 cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits, size_t npixels,
 		ByteMap *d_summary, void *d_workspace, cudaStream_t stream);

@@ -41,14 +41,13 @@ cudaError_t launch_prepass_none(const void *d_src, int srccomps, int alphabits, 
 // =====================================================================================================
 // DITHER_SIMPLE (reference s2tc_algorithm.cpp:1307-1349): one carry per channel runs through the whole
 // image in raster order.  Texels are cut into chunks of kChunk (one thread each), 128 chunks per CTA tile.
-//   phase 1  dither_maps_kernel : per chunk, the transfer map carry-in -> carry-out of every channel,
-//                                 built right to left with byte permutes (dither_core.cuh); a tree
-//                                 reduction inside the CTA composes them into the tile's map
-//   phase 2  dither_scan_kernel : one CTA composes / walks the tile maps from the true carry-in and leaves
+//   phase 1  dither_maps_kernel : per chunk, the transfer map carry-in -> carry-out of every channel, built right to
+//                                 left with byte permutes (dither_core.cuh); then a scan over the tile's 128 chunk
+//                                 maps: every chunk's EXCLUSIVE prefix map is stored, and the tile's map
+//   phase 2  scan_*_kernel      : compose / walk the tile maps from the true carry-in (three small launches) and leave
 //                                 every tile's starting carry (or, for sharding, the map of the whole range)
-//   phase 3  dither_apply_kernel: walks the tile's chunk maps to every chunk's carry, then every thread
-//                                 streams its own 512-byte chunk (128-bit loads/stores, 8 in flight) and
-//                                 replays the recurrence
+//   phase 3  dither_apply_kernel: carry entering a chunk = its prefix map applied to the tile's carry; the texels go
+//                                 through shared memory per warp (coalesced global access) and are replayed in place
 // =====================================================================================================
 constexpr int kChunk = 128;       // texels per thread
 constexpr int kTileThreads = 128; // chunks per CTA
@@ -286,137 +285,140 @@ dither_maps_kernel(const uint8_t *__restrict__ src, int srccomps, ChanKinds kind
 	}
 }
 
-// One CTA of 32 warps.  A warp holds a map with entry k in lane k, so composing two maps is ONE shuffle
-// (out[k] = second[first[k]] = shfl(second, first)) and applying a map to a carry is a broadcast shuffle.
-// summary == nullptr: carry[] (4 ints) is the carry into tile 0; writes tile_carry[tile][4] and leaves the
-// carry out of the last tile in carry[].  summary != nullptr: writes the composed maps of all tiles instead
-// (the "transfer function" of this texel range, exchanged between GPUs when a carry chain is sharded).
-constexpr int kScanThreads = 1024;
+// ---- phase 2: scan over the tile maps, three small launches ----------------------------------------------------
+// A warp holds a map with entry k in lane k, so composing two maps is one table lookup per lane
+// (out[k] = second[first[k]]) and following a carry is the same lookup in one lane.
+//   scan_partial_kernel : every warp composes the maps of its 32 tiles (grid: 256 tiles per CTA)
+//   scan_carry_kernel   : one CTA, one warp per channel (the kinds are different code paths), walks the partial
+//                         maps from the true carry-in and leaves the carry entering every warp's tiles -- or, for
+//                         sharding (summary != nullptr), folds them into the map of the whole range
+//   scan_walk_kernel    : every warp walks its 32 tiles from its carry and writes the carry entering each tile
+// (The first version did all three in ONE CTA of 32 warps: 0.076 ms for 4096 tiles, issue-bound on a single SM,
+// 17 % of the whole pre-pass by the time the other two phases had been tuned.)
+constexpr int kScanWarpTiles = 32;
+constexpr int kScanCtaWarps = 8;
+constexpr int kScanCtaTiles = kScanWarpTiles * kScanCtaWarps;
+constexpr int kCarryStage = 64; // partial maps the carry kernel stages in shared memory at a time
 
-constexpr int kScanStage = 8; // tile maps a warp stages in shared memory at a time (8 x 128 B = 1 KB per warp)
-
-// stage tile maps [first, first + kScanStage) of this warp's range: 4 coalesced 128-bit loads per lane, issued together
-__device__ __forceinline__ void scan_stage_load(const ByteMap *__restrict__ tilemaps, size_t first, size_t hi, int lane, uint4 (&regs)[kScanStage / 4])
+// this warp's tile maps -> its 4 KB of shared memory (coalesced 128-bit loads, zeros past the end)
+__device__ __forceinline__ void scan_load_warp_tiles(const ByteMap *__restrict__ tilemaps, size_t tile0, size_t ntiles, int lane, uint4 *s_warp)
 {
-	const uint4 *g = reinterpret_cast<const uint4 *>(tilemaps + first * 4); // 8 uint4 per tile (4 channels x 32 B)
+	const uint4 *g = reinterpret_cast<const uint4 *>(tilemaps + tile0 * 4); // 8 uint4 per tile (4 channels x 32 B)
 #pragma unroll
-	for (int q = 0; q < kScanStage / 4; ++q) {
-		const int idx = q * 32 + lane; // 8 uint4 per tile
-		regs[q] = first + (size_t) (idx >> 3) < hi ? __ldg(g + idx) : make_uint4(0, 0, 0, 0);
+	for (int q = 0; q < kScanWarpTiles * 8 / 32; ++q) {
+		const int idx = q * 32 + lane;
+		s_warp[idx] = tile0 + (size_t) (idx >> 3) < ntiles ? __ldg(g + idx) : make_uint4(0, 0, 0, 0);
 	}
+	__syncwarp();
 }
 
-__global__ void __launch_bounds__(kScanThreads)
-dither_scan_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKinds kinds, int *carry,
-		int *__restrict__ tile_carry, ByteMap *summary)
+__global__ void __launch_bounds__(kScanCtaWarps * 32)
+scan_partial_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKinds kinds, uint8_t *__restrict__ parts /* [warps][4][32] */)
 {
-	__shared__ uint8_t s_part[32][4][32];                 // map of each warp's tiles
-	__shared__ int s_start[32][4];                        // carry entering each warp's tiles
-	__shared__ __align__(16) uint8_t s_stage[32][kScanStage][4][32]; // per warp: staged tile maps
+	__shared__ __align__(16) uint8_t s_tiles[kScanCtaWarps][kScanWarpTiles][4][32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const size_t per = (ntiles + 31) / 32;
-	const size_t lo = min(ntiles, (size_t) warp * per), hi = min(ntiles, lo + per);
-	bool shift[4], bit1[4];
-	int radius[4];
-#pragma unroll
-	for (int ch = 0; ch < 4; ++ch) {
-		shift[ch] = kinds.k[ch] <= kChanShift4;
-		bit1[ch] = kinds.k[ch] == kChanBit1;
-		radius[ch] = chan_radius(kinds.k[ch]);
-	}
-	uint4 *stage4 = reinterpret_cast<uint4 *>(&s_stage[warp][0][0][0]);
-
-	// phase A: compose this warp's tile maps; acc[ch] = entry `lane` of the composition (bit1: running sum mod 255)
-	int acc[4];
-#pragma unroll
-	for (int ch = 0; ch < 4; ++ch)
-		acc[ch] = bit1[ch] ? 0 : lane;
-	{
-		uint4 regs[kScanStage / 4];
-		scan_stage_load(tilemaps, lo, hi, lane, regs);
-		for (size_t base = lo; base < hi; base += kScanStage) {
-			__syncwarp();
-#pragma unroll
-			for (int q = 0; q < kScanStage / 4; ++q)
-				stage4[q * 32 + lane] = regs[q];
-			__syncwarp();
-			if (base + kScanStage < hi)
-				scan_stage_load(tilemaps, base + kScanStage, hi, lane, regs); // in flight while this stage is consumed
-			const int cnt = (int) min((size_t) kScanStage, hi - base);
-			for (int i = 0; i < cnt; ++i) {
-#pragma unroll
-				for (int ch = 0; ch < 4; ++ch) {
-					if (shift[ch])
-						acc[ch] = s_stage[warp][i][ch][acc[ch] & 31]; // out[k] = tile[acc[k]]
-					else if (bit1[ch])
-						acc[ch] = (acc[ch] + s_stage[warp][i][ch][0]) % 255;
-				}
-			}
-		}
-	}
-#pragma unroll
-	for (int ch = 0; ch < 4; ++ch)
-		s_part[warp][ch][lane] = (uint8_t) acc[ch];
-	__syncthreads();
-
-	if (warp == 0) {
-		if (summary) { // fold the 32 partial maps, entry `lane` per lane
-#pragma unroll
-			for (int ch = 0; ch < 4; ++ch) {
-				int v = bit1[ch] ? 0 : lane;
-				if (shift[ch] || bit1[ch])
-					for (int w = 0; w < 32; ++w)
-						v = bit1[ch] ? (v + s_part[w][ch][0]) % 255 : s_part[w][ch][v & 31];
-				const int ns = chan_states(kinds.k[ch]);
-				summary[ch].e[lane] = (uint8_t) ((bit1[ch] ? lane == 0 : lane < ns) ? v : 0);
-			}
-		} else if (lane < 4) { // phase B: the carry entering each warp's range
-			const int kind = kinds.k[lane];
-			int c = carry[lane];
-			for (int w = 0; w < 32; ++w) {
-				s_start[w][lane] = c;
-				if (kind == kChanBit1)
-					c = balanced255(c + s_part[w][lane][0]);
-				else if (kind <= kChanShift4)
-					c = (int) s_part[w][lane][c + chan_radius(kind)] - chan_radius(kind);
-				else
-					c = 0;
-			}
-			carry[lane] = c;
-		}
-	}
-	if (summary)
+	const size_t gw = (size_t) blockIdx.x * kScanCtaWarps + warp;
+	const size_t tile0 = gw * kScanWarpTiles;
+	if (tile0 >= ntiles)
 		return;
-	__syncthreads();
-
-	// phase C: walk this warp's tiles from its carry (all lanes carry the same value; lanes 0..3 store)
-	int c[4];
+	scan_load_warp_tiles(tilemaps, tile0, ntiles, lane, reinterpret_cast<uint4 *>(&s_tiles[warp][0][0][0]));
+	const int cnt = (int) min((size_t) kScanWarpTiles, ntiles - tile0);
+	uint32_t acc[4];
 #pragma unroll
 	for (int ch = 0; ch < 4; ++ch)
-		c[ch] = s_start[warp][ch];
-	{
-		uint4 regs[kScanStage / 4];
-		scan_stage_load(tilemaps, lo, hi, lane, regs);
-		for (size_t base = lo; base < hi; base += kScanStage) {
-			__syncwarp();
+		acc[ch] = kinds.k[ch] == kChanBit1 ? 0u : (uint32_t) lane;
+	for (int i = 0; i < cnt; ++i) {
 #pragma unroll
-			for (int q = 0; q < kScanStage / 4; ++q)
-				stage4[q * 32 + lane] = regs[q];
-			__syncwarp();
-			if (base + kScanStage < hi)
-				scan_stage_load(tilemaps, base + kScanStage, hi, lane, regs);
-			const int cnt = (int) min((size_t) kScanStage, hi - base);
-			for (int i = 0; i < cnt; ++i) {
-				if (lane < 4)
-					tile_carry[(base + i) * 4 + lane] = lane == 0 ? c[0] : (lane == 1 ? c[1] : (lane == 2 ? c[2] : c[3]));
-#pragma unroll
-				for (int ch = 0; ch < 4; ++ch) {
-					if (shift[ch])
-						c[ch] = (int) s_stage[warp][i][ch][c[ch] + radius[ch]] - radius[ch];
-					else if (bit1[ch])
-						c[ch] = balanced255(c[ch] + s_stage[warp][i][ch][0]);
-				}
+		for (int ch = 0; ch < 4; ++ch) {
+			if (kinds.k[ch] <= kChanShift4)
+				acc[ch] = s_tiles[warp][i][ch][acc[ch]]; // out[k] = tile[acc[k]]
+			else if (kinds.k[ch] == kChanBit1) {
+				acc[ch] += s_tiles[warp][i][ch][0];
+				acc[ch] = acc[ch] >= 255u ? acc[ch] - 255u : acc[ch];
 			}
+		}
+	}
+#pragma unroll
+	for (int ch = 0; ch < 4; ++ch)
+		parts[(gw * 4 + ch) * 32 + lane] = (uint8_t) acc[ch];
+}
+
+__global__ void __launch_bounds__(128)
+scan_carry_kernel(const uint8_t *__restrict__ parts, size_t nparts, ChanKinds kinds, int *carry, int *__restrict__ starts /* [nparts][4] */,
+		ByteMap *summary)
+{
+	__shared__ __align__(16) uint8_t s_parts[kCarryStage][4][32];
+	const int lane = threadIdx.x & 31, ch = threadIdx.x >> 5; // one warp per channel
+	const int kind = kinds.k[ch];
+	const int r = chan_radius(kind);
+	// shift kinds: table index followed by this lane (summary: lane k follows state k; carry: every lane the carry);
+	// 1-bit kind: residue of the running sum, biased by 127 in carry mode so that it stays in [0, 254]
+	uint32_t v = kind <= kChanShift4 ? (summary ? (uint32_t) lane : (uint32_t) (carry[ch] + r))
+			: (kind == kChanBit1 ? (summary ? 0u : (uint32_t) (carry[ch] + 127)) : 0u);
+	for (size_t base = 0; base < nparts; base += kCarryStage) {
+		const int cnt = (int) min((size_t) kCarryStage, nparts - base);
+		__syncthreads();
+		{
+			const uint4 *g = reinterpret_cast<const uint4 *>(parts + base * 128);
+			uint4 *sp = reinterpret_cast<uint4 *>(&s_parts[0][0][0]);
+			for (int i = threadIdx.x; i < cnt * 8; i += 128)
+				sp[i] = __ldg(g + i);
+		}
+		__syncthreads();
+		if (kind <= kChanShift4) {
+			for (int i = 0; i < cnt; ++i) {
+				if (!summary && lane == 0)
+					starts[(base + i) * 4 + ch] = (int) v - r;
+				v = s_parts[i][ch][v & 31u];
+			}
+		} else if (kind == kChanBit1) {
+			for (int i = 0; i < cnt; ++i) {
+				if (!summary && lane == 0)
+					starts[(base + i) * 4 + ch] = (int) v - 127;
+				v += s_parts[i][ch][0];
+				v = v >= 255u ? v - 255u : v;
+			}
+		} else if (!summary && lane == 0) {
+			for (int i = 0; i < cnt; ++i)
+				starts[(base + i) * 4 + ch] = 0;
+		}
+	}
+	if (summary) {
+		const int ns = chan_states(kind);
+		summary[ch].e[lane] = (uint8_t) ((kind == kChanBit1 ? lane == 0 : lane < ns) ? v : 0u);
+	} else if (lane == 0)
+		carry[ch] = kind <= kChanShift4 ? (int) v - r : (kind == kChanBit1 ? (int) v - 127 : 0);
+}
+
+__global__ void __launch_bounds__(kScanCtaWarps * 32)
+scan_walk_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKinds kinds, const int *__restrict__ starts,
+		int *__restrict__ tile_carry)
+{
+	__shared__ __align__(16) uint8_t s_tiles[kScanCtaWarps][kScanWarpTiles][4][32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const size_t gw = (size_t) blockIdx.x * kScanCtaWarps + warp;
+	const size_t tile0 = gw * kScanWarpTiles;
+	if (tile0 >= ntiles)
+		return;
+	scan_load_warp_tiles(tilemaps, tile0, ntiles, lane, reinterpret_cast<uint4 *>(&s_tiles[warp][0][0][0]));
+	const int cnt = (int) min((size_t) kScanWarpTiles, ntiles - tile0);
+	// lane ch (< 4) follows channel ch; the others idle (32 steps of one dependent lookup each)
+	if (lane < 4) {
+		const int ch = lane, kind = kinds.k[ch];
+		const int r = chan_radius(kind);
+		const int c0 = starts[gw * 4 + ch];
+		uint32_t v = kind <= kChanShift4 ? (uint32_t) (c0 + r) : (uint32_t) (c0 + 127);
+		for (int i = 0; i < cnt; ++i) {
+			int c = 0;
+			if (kind <= kChanShift4) {
+				c = (int) v - r;
+				v = s_tiles[warp][i][ch][v & 31u];
+			} else if (kind == kChanBit1) {
+				c = (int) v - 127;
+				v += s_tiles[warp][i][ch][0];
+				v = v >= 255u ? v - 255u : v;
+			}
+			tile_carry[(tile0 + i) * 4 + ch] = c;
 		}
 	}
 }
@@ -599,11 +601,23 @@ dither_small_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits
 
 static size_t dither_tiles(size_t npixels) { return (npixels + kTilePixels - 1) / kTilePixels; }
 
-// workspace: chunk maps [tiles*128][4] | tile maps [tiles][4] | tile carries [tiles][4]
+// kernel launches of launch_prepass_simple (for the launch counters): one fused CTA for images of at most one tile,
+// else maps (unless ready) + three scan launches + replay
+int prepass_simple_launches(size_t npixels, bool maps_ready)
+{
+	if (!npixels)
+		return 0;
+	return !maps_ready && npixels <= (size_t) kTilePixels ? 1 : (maps_ready ? 4 : 5);
+}
+
+static size_t scan_parts_count(size_t tiles) { return (tiles + 31) / 32; } // = kScanWarpTiles tiles per partial map
+
+// workspace: chunk prefix maps [tiles*128][4] | tile maps [tiles][4] | tile carries [tiles][4] | scan: partial maps
+// [parts][4][32] bytes | scan: carries entering each part [parts][4]
 size_t dither_workspace_bytes(size_t npixels)
 {
-	const size_t tiles = dither_tiles(npixels);
-	return (tiles * kTileThreads * 4 + tiles * 4) * sizeof(ByteMap) + tiles * 4 * sizeof(int) + 64;
+	const size_t tiles = dither_tiles(npixels), parts = scan_parts_count(tiles);
+	return (tiles * kTileThreads * 4 + tiles * 4) * sizeof(ByteMap) + tiles * 4 * sizeof(int) + parts * (128 + 4 * sizeof(int)) + 256;
 }
 
 static const DitherLut *device_dither_lut(cudaError_t *err)
@@ -637,6 +651,8 @@ static cudaError_t run_dither(int phases, const void *d_src, int srccomps, int a
 	ByteMap *chunkmaps = (ByteMap *) d_workspace;
 	ByteMap *tilemaps = chunkmaps + tiles * kTileThreads * 4;
 	int *tile_carry = (int *) (tilemaps + tiles * 4);
+	uint8_t *scan_parts = (uint8_t *) (((uintptr_t) (tile_carry + tiles * 4) + 15) & ~(uintptr_t) 15);
+	int *scan_starts = (int *) (scan_parts + scan_parts_count(tiles) * 128);
 	const ChanKinds kinds = chan_kinds(srccomps, alphabits);
 	cudaError_t e;
 	const DitherLut *lut = device_dither_lut(&e);
@@ -650,8 +666,15 @@ static cudaError_t run_dither(int phases, const void *d_src, int srccomps, int a
 	if (phases & 1)
 		dither_maps_kernel<<<(unsigned) tiles, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, kinds, npixels, lut,
 				65536u, chunkmaps, tilemaps);
-	if (phases & 2)
-		dither_scan_kernel<<<1, kScanThreads, 0, stream>>>(tilemaps, tiles, kinds, d_carry, tile_carry, d_summary);
+	if (phases & 2) {
+		static_assert(kScanWarpTiles == 32, "scan_parts_count");
+		const size_t nparts = scan_parts_count(tiles);
+		const unsigned ctas = (unsigned) ((tiles + kScanCtaTiles - 1) / kScanCtaTiles);
+		scan_partial_kernel<<<ctas, kScanCtaWarps * 32, 0, stream>>>(tilemaps, tiles, kinds, scan_parts);
+		scan_carry_kernel<<<1, 128, 0, stream>>>(scan_parts, nparts, kinds, d_carry, scan_starts, d_summary);
+		if (!d_summary)
+			scan_walk_kernel<<<ctas, kScanCtaWarps * 32, 0, stream>>>(tilemaps, tiles, kinds, scan_starts, tile_carry);
+	}
 	if (phases & 4)
 		dither_apply_kernel<<<(unsigned) tiles, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, alphabits,
 				kinds, npixels, chunkmaps, tile_carry, (uint32_t *) d_reduced);
