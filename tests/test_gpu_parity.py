@@ -143,6 +143,19 @@ def test_prepass_and_block_api(encoder):
         assert np.array_equal(got, want), (cd, nr, rf)
 
 
+def test_dither_simple_awkward_sizes(encoder):
+    """DITHER_SIMPLE at sizes that leave partial chunks, partial warps and partial tiles (the replay stages whole warps
+    through shared memory and falls back otherwise; the scan hands 32 tiles to a warp, 256 to a CTA), 3-component
+    sources, and more tiles than one carry-stage holds (64 partial maps = 2048 tiles)."""
+    for img in (synth.synth_noise(1000, 700, seed=31), synth.synth_noise(333, 257, seed=32), synth.synth_rgba(2048, 520, seed=33),
+                synth.synth_noise(300, 200, seed=34, comps=3), synth.synth_noise(127, 129, seed=35),
+                synth.synth_noise(4096, 8200, seed=36)):
+        for ab in (1, 4, 8):
+            assert np.array_equal(encoder.rgb565_image(img, ab, 1), O.orc_prepass(img, ab, 1)), (img.shape, ab)
+        if img.shape[0] * img.shape[1] < 2_000_000:
+            _cmp(encoder, img, O.DXT1, O.WAVG, -1, O.ALWAYS, O.DITHER_SIMPLE)
+
+
 def test_floyd_steinberg_bands(encoder):
     """DITHER_FLOYDSTEINBERG across band boundaries (32 rows per warp), odd/even heights (the alpha pass is seeded
     from the red channel's last row differently), widths smaller than the 2-texel row skew, 3-component sources."""
