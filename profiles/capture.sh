@@ -21,7 +21,7 @@ full config2_search16_finish "search16|finish_kernel" 9 3
 launches config3_4096 --workload config3 --size 4096
 full config3_search_cand_finish "pair_search|random_cand|finish_kernel" 3 3 --workload config3 --size 4096
 launches defaults --workload defaults
-full defaults_fast_dither "fast_encode|dither_" 4 4 --workload defaults
+full defaults_fast_dither "fast_encode|dither_|scan_" 6 6 --workload defaults
 launches config5 --workload config5
 full config5_search16_finish "search16|finish_kernel" 9 3 --workload config5
 ls -la $OUT
