@@ -87,8 +87,13 @@ void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, 
 	}
 	const size_t nchunks = (npix + kChunk - 1) / kChunk;
 	const size_t ntiles = (nchunks + kTileChunks - 1) / kTileChunks;
+	// chunkmap[chunk][0..2]: EXCLUSIVE prefix maps of the colour channels inside the tile (composition of the tile's
+	// earlier chunks), [3]: alpha -- prefix sum mod 255 (1-bit kind) or the chunk's own 31-state map (DXT3)
 	std::vector<ByteMap> chunkmap(ntiles * kTileChunks * 4), tilemap(ntiles * 4);
-	for (size_t chunk = 0; chunk < ntiles * kTileChunks; ++chunk) { // phase 1: right-to-left PRMT composition
+	std::vector<RgbTables> tabs(ntiles * kTileChunks);
+	std::vector<uint32_t> asums(ntiles * kTileChunks);
+	std::vector<ByteMap> amaps(ntiles * kTileChunks);
+	for (size_t chunk = 0; chunk < ntiles * kTileChunks; ++chunk) { // phase 1a: right-to-left PRMT composition per chunk
 		const size_t first = chunk * kChunk;
 		const int count = first >= npix ? 0 : (int) std::min<size_t>(kChunk, npix - first);
 		RgbTables tab;
@@ -110,32 +115,104 @@ void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, 
 			for (int i = count; i > 0; --i)
 				rgb_tables_prepend(tab, wide[first + i - 1], lut.lut3, lut.lut2);
 		}
-		ByteMap *m = &chunkmap[chunk * 4];
-		rgb_tables_store(tab, m[0], m[1], m[2]);
+		tabs[chunk] = tab;
+		asums[chunk] = asum;
+		memset(amaps[chunk].e, 0, sizeof(amaps[chunk].e));
 		if (kinds.k[3] == kChanShift4)
-			alpha_map_of_run(m[3], kChanShift4, (const uint8_t *) (wide.data() + (count ? first : 0)) + 3, 4, count);
-		else {
-			memset(m[3].e, 0, sizeof(m[3].e));
-			m[3].e[0] = (uint8_t) (asum % 255u);
+			alpha_map_of_run(amaps[chunk], kChanShift4, (const uint8_t *) (wide.data() + (count ? first : 0)) + 3, 4, count);
+	}
+	for (size_t t = 0; t < ntiles; ++t) { // phase 1b: the kernel's scan over the tile's chunk tables
+		RgbTables incl[kTileChunks];
+		uint32_t aincl[kTileChunks];
+		for (int k = 0; k < kTileChunks; ++k) {
+			incl[k] = tabs[t * kTileChunks + k];
+			aincl[k] = asums[t * kTileChunks + k];
+		}
+		for (int w = 0; w < kTileChunks / 32; ++w) // Kogge-Stone inside every group of 32 chunks (a warp)
+			for (int delta = 1; delta < 32; delta <<= 1) {
+				RgbTables next[32];
+				uint32_t anext[32];
+				for (int l = 0; l < 32; ++l) {
+					next[l] = incl[w * 32 + l];
+					anext[l] = aincl[w * 32 + l];
+					if (l >= delta) {
+						rgb_tables_join(next[l], incl[w * 32 + l - delta], incl[w * 32 + l]);
+						anext[l] += aincl[w * 32 + l - delta];
+					}
+				}
+				for (int l = 0; l < 32; ++l) {
+					incl[w * 32 + l] = next[l];
+					aincl[w * 32 + l] = anext[l];
+				}
+			}
+		for (int k = 0; k < kTileChunks; ++k) {
+			const int w = k / 32, l = k % 32;
+			RgbTables excl, left;
+			rgb_tables_init(left);
+			uint32_t aexcl = aincl[k] - asums[t * kTileChunks + k];
+			for (int v = 0; v < w; ++v) { // the warps to the left
+				RgbTables both;
+				rgb_tables_join(both, left, incl[v * 32 + 31]);
+				left = both;
+				aexcl += aincl[v * 32 + 31];
+			}
+			if (l == 0)
+				rgb_tables_init(excl);
+			else
+				excl = incl[k - 1];
+			if (w > 0) {
+				RgbTables both;
+				rgb_tables_join(both, left, excl);
+				excl = both;
+			}
+			ByteMap *m = &chunkmap[(t * kTileChunks + k) * 4];
+			rgb_tables_store(excl, m[0], m[1], m[2]);
+			if (kinds.k[3] == kChanShift4)
+				m[3] = amaps[t * kTileChunks + k];
+			else {
+				memset(m[3].e, 0, sizeof(m[3].e));
+				m[3].e[0] = (uint8_t) (aexcl % 255u);
+			}
+			if (k == kTileChunks - 1) { // the last chunk's inclusive prefix is the tile's map
+				RgbTables whole;
+				rgb_tables_join(whole, left, incl[k]);
+				ByteMap *tm = &tilemap[t * 4];
+				rgb_tables_store(whole, tm[0], tm[1], tm[2]);
+				memset(tm[3].e, 0, sizeof(tm[3].e));
+				tm[3].e[0] = (uint8_t) ((aexcl + asums[t * kTileChunks + k]) % 255u);
+			}
+		}
+		if (kinds.k[3] == kChanShift4) { // 31-state alpha maps: composed one by one
+			ByteMap acc;
+			bmap_identity(acc, kChanShift4);
+			for (int k = 0; k < kTileChunks; ++k) {
+				ByteMap r = acc;
+				bmap_compose(r, acc, amaps[t * kTileChunks + k], kChanShift4);
+				acc = r;
+			}
+			tilemap[t * 4 + 3] = acc;
 		}
 	}
-	for (size_t t = 0; t < ntiles; ++t)
+	// phase 2: partial maps of 32 tiles each, walked from the carry; then the tiles of every part
+	const size_t nparts = (ntiles + 31) / 32;
+	std::vector<ByteMap> parts(nparts * 4);
+	for (size_t p = 0; p < nparts; ++p)
 		for (int ch = 0; ch < 4; ++ch) {
 			ByteMap acc;
 			bmap_identity(acc, kinds.k[ch]);
-			for (int k = 0; k < kTileChunks; ++k) {
+			for (size_t t = p * 32; t < std::min(ntiles, p * 32 + 32); ++t) {
 				ByteMap r = acc;
-				bmap_compose(r, acc, chunkmap[(t * kTileChunks + k) * 4 + ch], kinds.k[ch]);
+				bmap_compose(r, acc, tilemap[t * 4 + ch], kinds.k[ch]);
 				acc = r;
 			}
-			tilemap[t * 4 + ch] = acc;
+			parts[p * 4 + ch] = acc;
 		}
-	if (summary) { // transfer function of the whole range = composition of the tile maps
+	if (summary) { // transfer function of the whole range = composition of the partial maps
 		for (int ch = 0; ch < 4; ++ch) {
 			bmap_identity(summary[ch], kinds.k[ch]);
-			for (size_t t = 0; t < ntiles; ++t) {
+			for (size_t p = 0; p < nparts; ++p) {
 				ByteMap r = summary[ch];
-				bmap_compose(r, summary[ch], tilemap[t * 4 + ch], kinds.k[ch]);
+				bmap_compose(r, summary[ch], parts[p * 4 + ch], kinds.k[ch]);
 				summary[ch] = r;
 			}
 		}
@@ -145,23 +222,33 @@ void prepass(const uint8_t *src, int comps, int abits, int dither, size_t npix, 
 	if (carry_io)
 		memcpy(carry, carry_io, sizeof(carry));
 	std::vector<int> tile_carry(ntiles * 4);
-	for (size_t t = 0; t < ntiles; ++t) // phase 2
+	for (size_t p = 0; p < nparts; ++p)
 		for (int ch = 0; ch < 4; ++ch) {
-			tile_carry[t * 4 + ch] = carry[ch];
-			carry[ch] = bmap_apply(tilemap[t * 4 + ch], kinds.k[ch], carry[ch]);
+			int c = carry[ch]; // carry entering the part
+			for (size_t t = p * 32; t < std::min(ntiles, p * 32 + 32); ++t) {
+				tile_carry[t * 4 + ch] = c;
+				c = bmap_apply(tilemap[t * 4 + ch], kinds.k[ch], c);
+			}
+			carry[ch] = bmap_apply(parts[p * 4 + ch], kinds.k[ch], carry[ch]);
 		}
 	if (carry_io)
 		memcpy(carry_io, carry, sizeof(carry));
-	for (size_t t = 0; t < ntiles; ++t) { // phase 3: walk the chunk maps, replay every chunk
-		int c[4] = {tile_carry[t * 4], tile_carry[t * 4 + 1], tile_carry[t * 4 + 2], tile_carry[t * 4 + 3]};
+	for (size_t t = 0; t < ntiles; ++t) { // phase 3: carry entering a chunk = its prefix map applied to the tile's carry
+		int ac = tile_carry[t * 4 + 3]; // DXT3 alpha only: walked through the per-chunk maps
 		for (int k = 0; k < kTileChunks; ++k) {
 			const size_t chunk = t * kTileChunks + k, first = chunk * kChunk;
 			const int count = first >= npix ? 0 : (int) std::min<size_t>(kChunk, npix - first);
-			int cc[4] = {c[0], c[1], c[2], c[3]};
+			const ByteMap *m = &chunkmap[chunk * 4];
+			int cc[4];
+			for (int ch = 0; ch < 3; ++ch)
+				cc[ch] = bmap_apply(m[ch], kinds.k[ch], tile_carry[t * 4 + ch]);
+			if (kinds.k[3] == kChanShift4) {
+				cc[3] = ac;
+				ac = bmap_apply(m[3], kChanShift4, ac);
+			} else
+				cc[3] = bmap_apply(m[3], kinds.k[3], tile_carry[t * 4 + 3]);
 			for (int i = 0; i < count; ++i)
 				wide[first + i] = replay_texel(cc, wide[first + i], kinds.k[3], comps == 4, abits);
-			for (int ch = 0; ch < 4; ++ch)
-				c[ch] = bmap_apply(chunkmap[chunk * 4 + ch], kinds.k[ch], c[ch]);
 		}
 	}
 	memcpy(out, wide.data(), npix * 4);

@@ -79,7 +79,8 @@ def test_whole_pipeline_against_oracle():
 def test_dither_simple_large_and_ragged():
     """Chunk/tile boundaries of the carry scan: > 1 tile (16384 texels), ragged last chunk, saturated values."""
     for img in (synth.synth_noise(300, 131, seed=2), synth.synth_rgba(257, 129, seed=3),
-                np.full((70, 250, 4), 255, np.uint8), synth.synth_noise(190, 90, seed=6, comps=3)):
+                np.full((70, 250, 4), 255, np.uint8), synth.synth_noise(190, 90, seed=6, comps=3),
+                synth.synth_noise(1000, 600, seed=7)):   # 37 tiles: two parts of the scan
         h, w, c = img.shape
         for ab in (1, 4, 8):
             got = np.zeros((h, w, 4), np.uint8)
