@@ -1,7 +1,7 @@
 // search16.inl -- MODE_NORMAL without random candidates (S2TC_RANDOM_COLORS = 0, or NORMALMAP with
-// the default -1): gather, distance matrix, c0/c1 pair search and the DXT5 alpha search in ONE kernel,
-// one thread per 4x4 block, everything in registers.  It writes the chosen endpoints; finish_kernel
-// (kernels_finish.cu) refines and packs them.
+// the default -1): gather, distance matrix and c0/c1 pair search (and, as a second launch of the same kernel,
+// the DXT5 alpha search), one thread per 4x4 block, everything in registers.  It writes the chosen
+// endpoints; finish_kernel (kernels_finish.cu) refines and packs them.
 //
 // Reference path per block: s2tc_algorithm.cpp:938-959 (gather), :997-1001 (single-colour hack), :367-414
 // (reduce_colors_inplace), :416-478 (reduce_colors_inplace_2fixpoints).
@@ -19,7 +19,8 @@
 // conflicts per LDS (r01a, 9.7 ms on config 2); the first register-resident version fused refinement and
 // packing into the same kernel (3.1 ms): its scans sat at ~90 % ALU-pipe utilisation with an idle FMA
 // pipe, and its refinement tail ran at 3 warps per scheduler.  Moving the adds to the FMA pipe, 16-bit
-// packed alpha rows and the split into search + finish kernels brought it to 1.75 + 0.73 ms.
+// packed alpha rows and the split into search + finish kernels brought it to 1.05 (colour) + 0.66 (alpha) +
+// 0.63 ms (finish); DESIGN.md 5.1 has the steps and what was measured and rejected.
 #include <utility>
 
 #include "kernels.cuh"
