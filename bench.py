@@ -146,7 +146,10 @@ def workload_config(args, wl):
     return {"workload": f"{args.workload}: {dxt_n} {width}x{height} {gen}, S2TC_COLORDIST_MODE={cd_n}, "
                         f"S2TC_RANDOM_COLORS={nrandom}, S2TC_REFINE_COLORS={refine_n}, S2TC_DITHER_MODE={args.dither}",
             "per_gpu_texture": f"{width}x{height} RGBA8", "sharding": "block rows of one tall texture, one shard per GPU",
-            "l2": f"inputs {width * height * 4 >> 20} MiB per GPU exceed the 126 MiB L2; no flush needed"}
+            "l2": (f"inputs {width * height * 4 >> 20} MiB per GPU exceed the 126 MiB L2; no flush needed"
+                   if width * height * 4 > (126 << 20) else
+                   f"inputs {width * height * 4 >> 20} MiB per GPU FIT the 126 MiB L2 (a --size/--workload choice for "
+                   f"debugging or profiling, not a bench configuration)")}
 
 
 def main():
