@@ -160,6 +160,21 @@ __device__ __forceinline__ uint32_t pair_key(const uint32_t (&a)[8], const uint3
 //   * Diagonal tiles hold 120 pairs: 4 per lane, both rows loaded per pair (the (jj, half) walk would spend 8 steps
 //     per lane on them at 47 % utilisation).
 // Only the last tile column can hold rows j >= m.  eight: the integer 8, opaque (see mad_opaque).
+// pair number p (lexicographic over i < j < 16) -> i | j << 8, padded to 128 entries
+struct DiagPairs {
+	uint16_t v[128];
+	constexpr DiagPairs() : v()
+	{
+		int p = 0;
+		for (int i = 0; i < 16; ++i)
+			for (int j = i + 1; j < 16; ++j)
+				v[p++] = (uint16_t) (i | (j << 8));
+		for (; p < 128; ++p)
+			v[p] = (uint16_t) (0 | (1 << 8));
+	}
+};
+__device__ const DiagPairs kDiagPairs{};
+
 template <int SUMBITS> struct KeyedScan {
 	static constexpr int kRankBits = 32 - SUMBITS;
 	const uint32_t *rows;
@@ -222,19 +237,11 @@ __device__ __forceinline__ uint32_t scan_tiles_keyed(const uint32_t *rows, int m
 			ks.template tile<true>(a, r1, r2, j1);
 		ks.template tile<false>(b - 1, r2, r2, j1 + 16); // tile row b - 1 is off-diagonal for column b only
 	}
-	// diagonal tiles
-	uint32_t dij[4]; // i | j << 8 inside a tile
+	// diagonal tiles: the lane's four pairs (i | j << 8 inside a tile) from the table of the 120 pairs in scan order
+	uint32_t dij[4];
 #pragma unroll
-	for (int q = 0; q < 4; ++q) {
-		int p = lane + 32 * q, i = 0;
-		if (p >= 120)
-			p = 0; // lanes 24..31 have no fourth pair: any valid pair, masked in diagonal()
-		while (p >= 15 - i) {
-			p -= 15 - i;
-			++i;
-		}
-		dij[q] = (uint32_t) i | ((uint32_t) (i + 1 + p) << 8);
-	}
+	for (int q = 0; q < 4; ++q)
+		dij[q] = __ldg(&kDiagPairs.v[lane + 32 * q]); // entries 120..127 repeat pair 0: masked in diagonal()
 	for (int b = 0; b < ntile; ++b)
 		ks.diagonal(b, dij);
 	uint32_t best = ks.best;
@@ -360,20 +367,17 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, uint32
 	__syncwarp();
 
 	// 2. gather in the reference's column-major order (ref :940-959); bit o = x*4+y
+	// lane o < 16 looks at texel (x, y) = (o >> 2, o & 3); one ballot gives the mask of gathered texels
 	const uint32_t valid = valid_mask(w, h);
-	uint32_t usemask = 0;
-#pragma unroll
-	for (int i = 0; i < 16; ++i) {
-		const uint32_t p = px[i];
-		bool use = (valid >> i) & 1u;
-		if (DXT == kDxt1)
-			use = use && (p >> 24) != 0;
-		if (use)
-			usemask |= 1u << ((i & 3) * 4 + (i >> 2));
-	}
+	const int ti = (lane & 3) * 4 + ((lane >> 2) & 3); // texel index y * 4 + x of lane o
+	const uint32_t mine = px[ti];
+	bool use = lane < 16 && ((valid >> ti) & 1u);
+	if (DXT == kDxt1)
+		use = use && (mine >> 24) != 0;
+	const uint32_t usemask = __ballot_sync(0xFFFFFFFFu, use);
 	int n = __popc(usemask);
-	if (lane < 16 && ((usemask >> lane) & 1u))
-		col[__popc(usemask & ((1u << lane) - 1u))] = px[(lane & 3) * 4 + (lane >> 2)];
+	if (use)
+		col[__popc(usemask & ((1u << lane) - 1u))] = mine;
 	if (n == 0) {
 		if (lane == 0)
 			col[0] = 0;
