@@ -318,6 +318,8 @@ int s2tc_b200_ctx_create(int device, s2tc_b200_ctx **out)
 	CU(cudaHostAlloc((void **) &c->h_block, 128, cudaHostAllocDefault));
 	CU(c->plans.reserve(sizeof(RandPlan) * kPlanRing));
 	CU(c->small.reserve(1024));
+	CU(init_all_luts(c->stream)); // device-side tables of the metrics (one copy per translation unit), on this device
+	CU(cudaStreamSynchronize(c->stream));
 	*out = c;
 	return 0;
 }

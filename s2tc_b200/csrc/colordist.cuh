@@ -154,14 +154,44 @@ template <> struct Metric<kSRGB> { // ref :269-283
 	}
 };
 
+// Y(c) of SRGB_MIXED (ref :292-294): int(sqrtf(37 * (84 r^2 + 72 g^2 + 28 b^2)) + 0.5f), individually rounded
+S2TC_HD int srgb_mixed_y(int r, int g, int b)
+{
+	int lin = 37 * (r * r * 84 + g * g * 72 + b * b * 28); // < 2^24: exact in fp32
+	return f_trunc(f_add(f_sqrt((float) lin), 0.5f));
+}
+
+#if defined(__CUDACC__) && defined(S2TC_USE_SRGB_MIXED_LUT)
+// Device builds of the per-block kernels read Y from a table of all 65536 RGB565 colours instead of running the
+// sqrtf chain per colour (~18 instructions, 16 + 2 per refinement pass of them per block).  One copy per translation
+// unit that opts in (no relocatable device code in this build), filled ON THE DEVICE by the formula above, so the
+// values are the kernel's own; S2TC_DEFINE_LUT_INIT(fn) defines the host function that fills this unit's copy and
+// s2tc_b200_ctx_create calls all of them.  Texels are always in the 5/6/5 domain here.
+static __device__ uint16_t g_srgb_mixed_y[65536];
+static __global__ void srgb_mixed_lut_kernel()
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x; // r | g << 5 | b << 11
+	g_srgb_mixed_y[idx] = (uint16_t) srgb_mixed_y(idx & 31, (idx >> 5) & 63, idx >> 11);
+}
+#define S2TC_DEFINE_LUT_INIT(fn)                                      \
+	cudaError_t fn(cudaStream_t stream)                               \
+	{                                                                 \
+		s2tc::srgb_mixed_lut_kernel<<<256, 256, 0, stream>>>();       \
+		return cudaGetLastError();                                    \
+	}
+#endif
+
 template <> struct Metric<kSRGB_MIXED> { // ref :285-315
 	typedef FeatRGB Feat; // {Y, U, V} of one colour
 	static constexpr bool kMayBeNegative = false;
 	static S2TC_HD Feat feat(uint32_t p)
 	{
-		int r = px_r(p), g = px_g(p), b = px_b(p);
-		int lin = 37 * (r * r * 84 + g * g * 72 + b * b * 28); // < 2^24: exact in fp32
-		int y = f_trunc(f_add(f_sqrt((float) lin), 0.5f));
+		int r = px_r(p), b = px_b(p);
+#if defined(__CUDA_ARCH__) && defined(S2TC_USE_SRGB_MIXED_LUT)
+		int y = __ldg(&g_srgb_mixed_y[(p & 31u) | ((p >> 3) & 0x7E0u) | ((p >> 5) & 0xF800u)]);
+#else
+		int y = srgb_mixed_y(r, px_g(p), b);
+#endif
 		return Feat{y, r * 191 - y, b * 191 - y};
 	}
 	static S2TC_HD int dist(const FeatRGB &a, const FeatRGB &b)

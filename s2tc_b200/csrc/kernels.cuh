@@ -96,6 +96,23 @@ __device__ __forceinline__ void load_block(const ImageView &v, int bx, int by, B
 }
 #endif
 
+// per-translation-unit lookup tables (colordist.cuh: S2TC_USE_SRGB_MIXED_LUT); a context fills all of them once
+cudaError_t init_luts_fast(cudaStream_t stream);
+cudaError_t init_luts_finish(cudaStream_t stream);
+cudaError_t init_luts_search(cudaStream_t stream);
+cudaError_t init_luts_search16_dxt1(cudaStream_t stream);
+cudaError_t init_luts_search16_dxt3(cudaStream_t stream);
+cudaError_t init_luts_search16_dxt5(cudaStream_t stream);
+inline cudaError_t init_all_luts(cudaStream_t stream)
+{
+	cudaError_t (*const fns[])(cudaStream_t) = {init_luts_fast, init_luts_finish, init_luts_search, init_luts_search16_dxt1,
+			init_luts_search16_dxt3, init_luts_search16_dxt5};
+	for (auto fn : fns)
+		if (cudaError_t e = fn(stream))
+			return e;
+	return cudaSuccess;
+}
+
 // ---- launch wrappers (defined in the .cu files); all asynchronous on `stream` -------------------
 
 // MODE_FAST: candidates + refinement + packing in one pass, one thread per block.

@@ -7,6 +7,7 @@
 // segment per texel row (4 x LDG.128 per thread) and writes 256 / 512 contiguous bytes
 // (STG.64 / STG.128).  Algorithmic traffic is 64 B in + 8|16 B out per block; the rest is integer
 // work (~500-600 ops per block), so this kernel sits near the HBM/ALU balance point.
+#define S2TC_USE_SRGB_MIXED_LUT
 #include "kernels.cuh"
 
 namespace s2tc {
@@ -61,5 +62,7 @@ cudaError_t launch_fast_encode(int dxt, int cd, int refine, const ImageView &v, 
 	default: return launch_fast_dxt<kDxt5>(cd, refine, v, d_out, stream);
 	}
 }
+
+S2TC_DEFINE_LUT_INIT(init_luts_fast)
 
 } // namespace s2tc

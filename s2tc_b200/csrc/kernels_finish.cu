@@ -2,6 +2,7 @@
 // block and produces the finished DXT block: equal-endpoint fix-ups, NEVER/ALWAYS/LOOP refinement,
 // DXT3/DXT5 alpha and packing (reference: s2tc_algorithm.cpp:1010-1107).  One thread per block; the
 // memory pattern is that of kernels_fast.cu plus one coalesced 8-byte endpoint read per block.
+#define S2TC_USE_SRGB_MIXED_LUT
 #include "kernels.cuh"
 
 namespace s2tc {
@@ -60,5 +61,7 @@ cudaError_t launch_finish(int dxt, int cd, int refine, const ImageView &v, const
 	default: return launch_finish_dxt<kDxt5>(cd, refine, v, d_ends, d_out, stream);
 	}
 }
+
+S2TC_DEFINE_LUT_INIT(init_luts_finish)
 
 } // namespace s2tc

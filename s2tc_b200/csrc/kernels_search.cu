@@ -24,6 +24,7 @@
 // Output: the chosen endpoints, 8 bytes per block; kernels_finish.cu turns them into DXT blocks.
 // History: the first version (32-bit rows, lanes striding j with 70 % utilisation) took 198 ms for the
 // 16.7 M blocks of config 3 (profiles/r01c).
+#define S2TC_USE_SRGB_MIXED_LUT
 #include "kernels.cuh"
 
 namespace s2tc {
@@ -535,5 +536,7 @@ cudaError_t launch_pair_search(int dxt, int cd, int nrandom, const ImageView &v,
 	default: return launch_search_dxt<kDxt5>(cd, nrandom, v, d_cand_c, d_cand_a, d_ends, stream);
 	}
 }
+
+S2TC_DEFINE_LUT_INIT(init_luts_search)
 
 } // namespace s2tc

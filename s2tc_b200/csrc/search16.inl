@@ -23,6 +23,7 @@
 // 0.63 ms (finish); DESIGN.md 5.1 has the steps and what was measured and rejected.
 #include <utility>
 
+#define S2TC_USE_SRGB_MIXED_LUT
 #include "kernels.cuh"
 
 namespace s2tc {
@@ -480,5 +481,7 @@ cudaError_t S2TC_SEARCH16_NAME(int cd, const ImageView &v, uint2 *d_ends, cudaSt
 {
 	return launch_search16_dxt<S2TC_SEARCH16_DXT>(cd, v, d_ends, stream);
 }
+
+S2TC_DEFINE_LUT_INIT(S2TC_SEARCH16_LUT_INIT)
 
 } // namespace s2tc
