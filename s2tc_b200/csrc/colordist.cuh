@@ -173,12 +173,6 @@ static __global__ void srgb_mixed_lut_kernel()
 	const int idx = blockIdx.x * blockDim.x + threadIdx.x; // r | g << 5 | b << 11
 	g_srgb_mixed_y[idx] = (uint16_t) srgb_mixed_y(idx & 31, (idx >> 5) & 63, idx >> 11);
 }
-#define S2TC_DEFINE_LUT_INIT(fn)                                      \
-	cudaError_t fn(cudaStream_t stream)                               \
-	{                                                                 \
-		s2tc::srgb_mixed_lut_kernel<<<256, 256, 0, stream>>>();       \
-		return cudaGetLastError();                                    \
-	}
 #endif
 
 template <> struct Metric<kSRGB_MIXED> { // ref :285-315
@@ -201,22 +195,52 @@ template <> struct Metric<kSRGB_MIXED> { // ref :285-315
 	}
 };
 
+// the unit vector of NORMALMAP (ref :321-336), every operation individually rounded
+S2TC_HD FeatF3 normalmap_dir(int r, int g, int b)
+{
+	float x = f_sub(f_mul(f_div((float) r, 31.0f), 2.0f), 1.0f);
+	float y = f_sub(f_mul(f_div((float) g, 63.0f), 2.0f), 1.0f);
+	float z = f_sub(f_mul(f_div((float) b, 31.0f), 2.0f), 1.0f);
+	float n = f_add(f_add(f_mul(x, x), f_mul(y, y)), f_mul(z, z));
+	if (n > 0) {
+		n = f_div(1.0f, f_sqrt(n));
+		x = f_mul(x, n);
+		y = f_mul(y, n);
+		z = f_mul(z, n);
+	}
+	return FeatF3{x, y, z};
+}
+
+#if defined(__CUDACC__) && defined(S2TC_USE_SRGB_MIXED_LUT)
+// same scheme as g_srgb_mixed_y: the unit vectors of all 65536 colours (three IEEE divisions, a square root and a
+// reciprocal per colour otherwise), 1 MB per opted-in translation unit, L2-resident
+static __device__ float4 g_normalmap_dir[65536];
+static __global__ void normalmap_lut_kernel()
+{
+	const int idx = blockIdx.x * blockDim.x + threadIdx.x; // r | g << 5 | b << 11
+	const FeatF3 d = normalmap_dir(idx & 31, (idx >> 5) & 63, idx >> 11);
+	g_normalmap_dir[idx] = make_float4(d.x, d.y, d.z, 0.0f);
+}
+#define S2TC_DEFINE_LUT_INIT(fn)                                      \
+	cudaError_t fn(cudaStream_t stream)                               \
+	{                                                                 \
+		s2tc::srgb_mixed_lut_kernel<<<256, 256, 0, stream>>>();       \
+		s2tc::normalmap_lut_kernel<<<256, 256, 0, stream>>>();        \
+		return cudaGetLastError();                                    \
+	}
+#endif
+
 template <> struct Metric<kNORMALMAP> { // ref :317-354
 	typedef FeatF3 Feat; // normalised direction
 	static constexpr bool kMayBeNegative = false;
 	static S2TC_HD Feat feat(uint32_t p)
 	{
-		float x = f_sub(f_mul(f_div((float) px_r(p), 31.0f), 2.0f), 1.0f);
-		float y = f_sub(f_mul(f_div((float) px_g(p), 63.0f), 2.0f), 1.0f);
-		float z = f_sub(f_mul(f_div((float) px_b(p), 31.0f), 2.0f), 1.0f);
-		float n = f_add(f_add(f_mul(x, x), f_mul(y, y)), f_mul(z, z));
-		if (n > 0) {
-			n = f_div(1.0f, f_sqrt(n));
-			x = f_mul(x, n);
-			y = f_mul(y, n);
-			z = f_mul(z, n);
-		}
-		return Feat{x, y, z};
+#if defined(__CUDA_ARCH__) && defined(S2TC_USE_SRGB_MIXED_LUT)
+		const float4 d = __ldg(&g_normalmap_dir[(p & 31u) | ((p >> 3) & 0x7E0u) | ((p >> 5) & 0xF800u)]);
+		return Feat{d.x, d.y, d.z};
+#else
+		return normalmap_dir(px_r(p), px_g(p), px_b(p));
+#endif
 	}
 	static S2TC_HD int dist(const FeatF3 &a, const FeatF3 &b)
 	{
