@@ -36,10 +36,12 @@ constexpr int kPitch32 = 20; // words per row, 32-bit distances (16 used)
 
 template <int CD> struct Packs16 { static constexpr bool value = CD == kAVG || CD == kWAVG || CD == kW0AVG; };
 
+// per-warp shared memory: texels [16] | exact rows [(mcap+16)][pitch] | quantised rows [(mcap+16)] x 16 B | c [(mcap+16)] |
+// colours [mcap] | features [mcap]
 __host__ __device__ inline size_t search_warp_bytes(int mcap, bool pack16, bool has_feat)
 {
 	const size_t rows = (size_t) (mcap + 16) * (pack16 ? kPitch16 : kPitch32) * 4; // +16: tile loads may touch one tile past m
-	size_t b = 64 + rows + (size_t) mcap * 4 + (has_feat ? (size_t) mcap * 12 : 0);
+	size_t b = 64 + rows + (size_t) (mcap + 16) * 20 + (size_t) mcap * 4 + (has_feat ? (size_t) mcap * 12 : 0);
 	return (b + 15) & ~(size_t) 15;
 }
 
@@ -131,36 +133,6 @@ template <> struct RowRegs<false> {
 // rank of pair (i, j), i < j < m, in the reference's lexicographic scan order
 __device__ __forceinline__ int pair_rank(int i, int j, int m) { return i * m - ((i * (i + 1)) >> 1) + (j - i - 1); }
 
-// a * b + c kept as an IMAD on the FMA pipe (b is a kernel argument the compiler cannot fold into a shift)
-__device__ __forceinline__ uint32_t mad_opaque(uint32_t a, uint32_t b, uint32_t c)
-{
-	uint32_t d;
-	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-	return d;
-}
-
-// Tile-local pair key (sum_k min(a[k], b[k]) << 3) | t.  Every horizontal add is an IDP.2A: 8 VIMNMX.U16x2 on the ALU
-// pipe, 8 IDP.2A + 1 IMAD on the FMA pipe, nothing else.  (With packed IADD3 adds in front of 3 IDP.2A the ALU pipe
-// bounded the kernel: 83 % busy against 25 % for the FMA pipe, profiles/r01g; this form is issue-bound, r01h.)
-__device__ __forceinline__ uint32_t pair_key(const uint32_t (&a)[8], const uint32_t (&b)[8], uint32_t eight, int t)
-{
-	uint32_t s = 0;
-#pragma unroll
-	for (int q = 0; q < 8; ++q)
-		s = __dp2a_lo(__vminu2(a[q], b[q]), 0x0101u, s);
-	return mad_opaque(s, eight, (uint32_t) t);
-}
-
-// Fast scan for 16-bit rows whose sums stay below 2^SUMBITS and whose pair count fits the remaining bits:
-// every pair becomes the single key (sum << RANKBITS) | rank, so "first minimum in (i, j) order" is an unsigned
-// min.  The pair triangle is cut into 16x16 tiles.
-//   * Off-diagonal tiles (every i < j): lane (jj, half) keeps row j of the tile column in registers and meets the 8 rows
-//     i = 16a + 8 half + t in increasing order, so inside a tile the key is (sum << 3) | t and the rank is attached
-//     once per tile.  Tile columns are taken two at a time (rows j and j + 16 in registers), so that one broadcast
-//     load of row i serves two pairs.
-//   * Diagonal tiles hold 120 pairs: 4 per lane, both rows loaded per pair (the (jj, half) walk would spend 8 steps
-//     per lane on them at 47 % utilisation).
-// Only the last tile column can hold rows j >= m.  eight: the integer 8, opaque (see mad_opaque).
 // pair number p (lexicographic over i < j < 16) -> i | j << 8, padded to 128 entries
 struct DiagPairs {
 	uint16_t v[128];
@@ -176,88 +148,204 @@ struct DiagPairs {
 };
 __device__ const DiagPairs kDiagPairs{};
 
-template <int SUMBITS> struct KeyedScan {
-	static constexpr int kRankBits = 32 - SUMBITS;
-	const uint32_t *rows;
-	int m, lane;
-	uint32_t eight;
-	uint32_t best = 0xFFFFFFFFu;
+// ---- pruned scan ---------------------------------------------------------------------------------------
+// The exact pair scan costs 16 min + 16 add per pair.  Most pairs are nowhere near the minimum, and a cheap LOWER
+// BOUND of a pair's sum shows it:  with q[i][k] = min(255, d[i][k] >> s)  (one byte per texel, 16 bytes per row)
+//     sum_k min(d[i][k], d[j][k])  >=  2^s * sum_k min(q[i][k], q[j][k])  =  2^s * (Rq[i] + Rq[j] - SAD(q[i], q[j])) / 2,
+// Rq = row sums, SAD = sum of absolute byte differences: four VABSDIFF4.U8.ACC per pair, 16 texels in 4 instructions.
+// A pair can only beat (or tie) the best exact sum T found so far if its bound is <= T; everything else is skipped
+// without ever being evaluated exactly.  The result is the reference's: every pair whose exact sum could be the
+// first minimum in (i, j) order is evaluated exactly and compared by (sum, rank).
+//   0. the 120 pairs of the first diagonal tile (the block's own colours) are scanned exactly: T, and from T the
+//      shift s (values above T never matter, so 8 bits cover [0, T] as finely as they can);
+//   1. every lane quantises rows: q bytes and c[i] = K - Rq[i];
+//   2. 16x16 tiles as before: lane (jj, half) keeps the q rows j of up to four tile columns in registers and meets the
+//      eight rows i = 16a + 8 half + t (broadcast loads).  acc = c[i] + SAD(q[i], q[j]) = K + Rq[j] - 2 bound, so the pair
+//      survives iff acc >= K + Rq[j] - 2 (T >> s), a per-lane constant: the loop only keeps max_t acc (VIMNMX3);
+//   3. after each group of tiles the (rare) lanes whose maximum passes walk their eight rows again, evaluate the
+//      surviving pairs exactly from the full-precision rows and the warp agrees on the new (T, rank).
+// Diagonal tiles go through the same loop (slots with i >= j only raise false alarms that step 3 discards); rows
+// beyond m are all-255 (bound = Rq[i], never better than a real pair of row i).
+// Measured on a B200 (tools_lab/ubench_sad.cu): VABSDIFF4 issues every other clock per scheduler on the ALU pipe,
+// so the bound costs ~9 clocks per pair against ~21 for the exact form.
+constexpr uint32_t kBoundBias = 4096; // K > 16 * 255
 
-	// tile row a against tile column(s) whose lane rows are r1 (row j1) and, if TWO, r2 (row j1 + 16)
-	template <bool TWO>
-	__device__ __forceinline__ void tile(int a, const RowRegs<true> &r1, const RowRegs<true> &r2, int j1)
-	{
-		const int i0 = 16 * a + 8 * (lane >> 4);
-		uint32_t t1 = 0xFFFFFFFFu, t2 = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c)
+{
+	uint32_t d;
+	asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+template <int NW> __device__ __forceinline__ uint32_t sad_row(const uint4 &a, const uint4 &b, uint32_t c)
+{
+	c = sad4(a.x, b.x, c);
+	if (NW > 1)
+		c = sad4(a.y, b.y, c);
+	if (NW > 2)
+		c = sad4(a.z, b.z, c);
+	if (NW > 3)
+		c = sad4(a.w, b.w, c);
+	return c;
+}
+
+// exact sum_k min(d[i][k], d[j][k]) from the full-precision rows
+template <bool PACK16> __device__ __forceinline__ uint32_t exact_pair_sum(const uint32_t *rows, int i, int j)
+{
+	RowRegs<PACK16> ri, rj;
+	ri.load(rows, i);
+	rj.load(rows, j);
+	if constexpr (PACK16) {
+		uint32_t s = 0;
 #pragma unroll
-		for (int t = 0; t < 8; ++t) {
-			RowRegs<true> ri;
-			ri.load(rows, i0 + t);
-			t1 = min(t1, pair_key(ri.w, r1.w, eight, t));
-			if (TWO)
-				t2 = min(t2, pair_key(ri.w, r2.w, eight, t));
-		}
-		if (j1 < m)
-			best = min(best, ((t1 >> 3) << kRankBits) + (uint32_t) pair_rank(i0 + (int) (t1 & 7u), j1, m));
-		if (TWO && j1 + 16 < m)
-			best = min(best, ((t2 >> 3) << kRankBits) + (uint32_t) pair_rank(i0 + (int) (t2 & 7u), j1 + 16, m));
+		for (int w = 0; w < 8; ++w)
+			s = __dp2a_lo(__vminu2(ri.w[w], rj.w[w]), 0x0101u, s);
+		return s;
+	} else {
+		return (uint32_t) pair_sum_32(ri.w, rj.w);
 	}
+}
 
-	// pairs number lane, lane + 32, lane + 64, lane + 96 (< 120) of diagonal tile b, numbered in lexicographic order
-	__device__ __forceinline__ void diagonal(int b, const uint32_t (&dij)[4])
+struct BestPair { // lexicographic (sum, rank): the reference's first minimum
+	uint32_t sum, rank;
+	__device__ __forceinline__ void take(uint32_t s, uint32_t r)
+	{
+		if (s < sum || (s == sum && r < rank)) {
+			sum = s;
+			rank = r;
+		}
+	}
+	__device__ __forceinline__ void warp_min()
 	{
 #pragma unroll
-		for (int q = 0; q < 4; ++q) {
-			const int i = 16 * b + (int) (dij[q] & 0xFFu), j = 16 * b + (int) (dij[q] >> 8);
-			RowRegs<true> ri, rj;
-			ri.load(rows, i);
-			rj.load(rows, j);
-			uint32_t sum = 0;
-#pragma unroll
-			for (int w = 0; w < 8; ++w)
-				sum = __dp2a_lo(__vminu2(ri.w[w], rj.w[w]), 0x0101u, sum);
-			if ((q < 3 || lane < 24) && j < m)
-				best = min(best, (sum << kRankBits) + (uint32_t) pair_rank(i, j, m));
+		for (int off = 16; off > 0; off >>= 1) {
+			const uint32_t os = __shfl_xor_sync(0xFFFFFFFFu, sum, off), orank = __shfl_xor_sync(0xFFFFFFFFu, rank, off);
+			take(os, orank);
 		}
 	}
 };
 
-template <int SUMBITS>
-__device__ __forceinline__ uint32_t scan_tiles_keyed(const uint32_t *rows, int m, int lane, uint32_t eight)
+// rows q of one lane for NC tile columns against the eight rows i0 .. i0+7: per-column maximum of acc
+template <int NW, int NC>
+__device__ __forceinline__ void bound_tile(const uint4 *q8, const uint32_t *cneg, int i0, const uint4 (&rj)[4], uint32_t (&mx)[4])
 {
-	KeyedScan<SUMBITS> ks{rows, m, lane, eight};
-	const int ntile = (m + 15) >> 4;
-	const int jj = lane & 15;
-	// off-diagonal tiles, columns from the right in pairs (b - 1, b)
-	for (int b = ntile - 1; b >= 1; b -= 2) {
-		const int j1 = 16 * (b - 1) + jj;
-		RowRegs<true> r1, r2;
-		r1.load(rows, j1);
-		r2.load(rows, j1 + 16);
-		for (int a = 0; a < b - 1; ++a)
-			ks.template tile<true>(a, r1, r2, j1);
-		ks.template tile<false>(b - 1, r2, r2, j1 + 16); // tile row b - 1 is off-diagonal for column b only
+#pragma unroll
+	for (int c = 0; c < 4; ++c)
+		mx[c] = 0;
+#pragma unroll 4
+	for (int t = 0; t < 8; t += 2) {
+		const uint4 qa = q8[i0 + t], qb = q8[i0 + t + 1];
+		const uint32_t ca = cneg[i0 + t], cb = cneg[i0 + t + 1];
+#pragma unroll
+		for (int c = 0; c < NC; ++c) {
+			const uint32_t x = sad_row<NW>(qa, rj[c], ca), y = sad_row<NW>(qb, rj[c], cb);
+			mx[c] = max(mx[c], max(x, y));
+		}
 	}
-	// diagonal tiles: the lane's four pairs (i | j << 8 inside a tile) from the table of the 120 pairs in scan order
-	uint32_t dij[4];
-#pragma unroll
-	for (int q = 0; q < 4; ++q)
-		dij[q] = __ldg(&kDiagPairs.v[lane + 32 * q]); // entries 120..127 repeat pair 0: masked in diagonal()
-	for (int b = 0; b < ntile; ++b)
-		ks.diagonal(b, dij);
-	uint32_t best = ks.best;
-#pragma unroll
-	for (int off = 16; off > 0; off >>= 1)
-		best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, off));
-	// rank -> (i, j): row i of the pair order starts at rank i (m - 1) - i (i - 1) / 2; every lane tests four rows
-	// (m <= 128) and the one that holds the rank announces itself
-	const int rank = (int) (best & ((1u << KeyedScan<SUMBITS>::kRankBits) - 1u));
-	uint32_t mine = 0;
+}
+
+// Returns (i << 16) | j of the winner in every lane.  rows: exact distance rows (16-bit packed, pitch kPitch16, or 32-bit,
+// pitch kPitch32; all values >= 0); q8 / cneg: workspace for 16 * ntile quantised rows.  n: columns in use.
+template <bool PACK16>
+__device__ __forceinline__ uint32_t scan_pruned(const uint32_t *rows, uint4 *q8, uint32_t *cneg, int m, int n, int lane, int sadj)
+{
+	const int ntile = (m + 15) >> 4;
+	const int jj = lane & 15, half = lane >> 4;
+	// 0. first diagonal tile, exactly
+	BestPair best{0xFFFFFFFFu, 0xFFFFFFFFu};
 #pragma unroll
 	for (int q = 0; q < 4; ++q) {
-		const int i = lane + 32 * q;
+		const uint32_t ij = __ldg(&kDiagPairs.v[lane + 32 * q]);
+		const int i = (int) (ij & 0xFFu), j = (int) (ij >> 8);
+		if ((q < 3 || lane < 24) && j < m)
+			best.take(exact_pair_sum<PACK16>(rows, i, j), (uint32_t) pair_rank(i, j, m));
+	}
+	best.warp_min();
+	if (best.sum != 0 || best.rank != 0) { // pair (0, 1) with sum 0 cannot be beaten
+		// 1. quantise
+		const int s = max(0, 32 - __clz(best.sum) - 8 + sadj);
+		for (int r = lane; r < 16 * ntile; r += 32) {
+			uint4 q = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+			if (r < m) {
+				uint32_t h[8];
+				if constexpr (PACK16) {
+					RowRegs<true> rr;
+					rr.load(rows, r);
+					const uint32_t mask = (0xFFFFu >> s) * 0x10001u;
+#pragma unroll
+					for (int w = 0; w < 8; ++w)
+						h[w] = __vminu2((rr.w[w] >> s) & mask, 0x00FF00FFu);
+				} else {
+					RowRegs<false> rr;
+					rr.load(rows, r);
+#pragma unroll
+					for (int w = 0; w < 8; ++w)
+						h[w] = min((uint32_t) rr.w[2 * w] >> s, 255u) | (min((uint32_t) rr.w[2 * w + 1] >> s, 255u) << 16);
+				}
+				q.x = __byte_perm(h[0], h[1], 0x6420);
+				q.y = __byte_perm(h[2], h[3], 0x6420);
+				q.z = __byte_perm(h[4], h[5], 0x6420);
+				q.w = __byte_perm(h[6], h[7], 0x6420);
+			}
+			q8[r] = q;
+			cneg[r] = kBoundBias - sad4(q.w, 0u, sad4(q.z, 0u, sad4(q.y, 0u, sad4(q.x, 0u, 0u))));
+		}
+		__syncwarp();
+		// 2./3. bound scan with exact evaluation of the survivors
+		const int nw = (n + 3) >> 2;
+		uint32_t tq2 = (best.sum >> s) * 2u;
+		for (int a = 0; a < ntile; ++a) {
+			const int i0 = 16 * a + 8 * half;
+			for (int b0 = a ? a : 1; b0 < ntile; b0 += 4) {
+				const int nc = min(4, ntile - b0);
+				uint4 rj[4];
+				uint32_t rq[4], mx[4];
+#pragma unroll
+				for (int c = 0; c < 4; ++c) {
+					const int j = 16 * (b0 + (c < nc ? c : 0)) + jj;
+					rj[c] = q8[j];
+					rq[c] = 2u * kBoundBias - cneg[j]; // K + Rq[j]
+				}
+				switch ((nw - 1) * 4 + nc - 1) {
+#define S2TC_BT(NW, NC) case (NW - 1) * 4 + NC - 1: bound_tile<NW, NC>(q8, cneg, i0, rj, mx); break;
+				S2TC_BT(1, 1) S2TC_BT(1, 2) S2TC_BT(1, 3) S2TC_BT(1, 4)
+				S2TC_BT(2, 1) S2TC_BT(2, 2) S2TC_BT(2, 3) S2TC_BT(2, 4)
+				S2TC_BT(3, 1) S2TC_BT(3, 2) S2TC_BT(3, 3) S2TC_BT(3, 4)
+				S2TC_BT(4, 1) S2TC_BT(4, 2) S2TC_BT(4, 3) default: bound_tile<4, 4>(q8, cneg, i0, rj, mx); break;
+#undef S2TC_BT
+				}
+				bool hit = false;
+#pragma unroll
+				for (int c = 0; c < 4; ++c) {
+					// survives iff acc >= K + Rq[j] - 2 (T >> s); signed: the right-hand side may be negative
+					const bool f = c < nc && (int) mx[c] >= (int) (rq[c] - tq2);
+					if (__any_sync(0xFFFFFFFFu, f)) {
+						hit = true;
+						if (f) {
+							const int j = 16 * (b0 + c) + jj;
+							const int thr = (int) (rq[c] - tq2);
+							for (int t = 0; t < 8; ++t) {
+								const int i = i0 + t;
+								const uint32_t acc = sad_row<4>(q8[i], rj[c], cneg[i]);
+								if ((int) acc >= thr && i < j && j < m)
+									best.take(exact_pair_sum<PACK16>(rows, i, j), (uint32_t) pair_rank(i, j, m));
+							}
+						}
+					}
+				}
+				if (hit) {
+					best.warp_min();
+					tq2 = (best.sum >> s) * 2u;
+				}
+			}
+		}
+	}
+	// rank -> (i, j): row i of the pair order starts at rank i (m - 1) - i (i - 1) / 2; every lane tests its rows and the
+	// one that holds the rank announces itself
+	const int rank = (int) best.rank;
+	uint32_t mine = 0;
+	for (int i = lane; i < m - 1; i += 32) {
 		const int start = i * (m - 1) - ((i * (i - 1)) >> 1);
-		if (i < m - 1 && rank >= start && rank < start + (m - 1 - i))
+		if (rank >= start && rank < start + (m - 1 - i))
 			mine = ((uint32_t) i << 16) | (uint32_t) (i + 1 + rank - start);
 	}
 	return __reduce_or_sync(0xFFFFFFFFu, mine);
@@ -333,7 +421,7 @@ __device__ __forceinline__ uint32_t scan_tiles(const uint32_t *rows, int m, int 
 
 template <int DXT, int CD>
 __global__ void __launch_bounds__(kSearchThreads)
-pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, uint32_t eight, const uint16_t *__restrict__ cand_c,
+pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, int sadj, const uint16_t *__restrict__ cand_c,
 		const uint8_t *__restrict__ cand_a, uint2 *__restrict__ ends)
 {
 	typedef Metric<CD> M;
@@ -350,7 +438,9 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, uint32
 	uint8_t *wbase = smem + (size_t) wi * warp_bytes;
 	uint32_t *px = reinterpret_cast<uint32_t *>(wbase);                                     // [16]
 	uint32_t *rows = reinterpret_cast<uint32_t *>(wbase + 64);                              // [(mcap+16)][kPitch]
-	uint32_t *col = rows + (size_t) (mcap + 16) * kPitch;                                   // [mcap]
+	uint4 *q8 = reinterpret_cast<uint4 *>(rows + (size_t) (mcap + 16) * kPitch);            // [(mcap+16)] quantised rows
+	uint32_t *cneg = reinterpret_cast<uint32_t *>(q8 + (mcap + 16));                        // [(mcap+16)]
+	uint32_t *col = cneg + (mcap + 16);                                                     // [mcap]
 	Feat *feat = reinterpret_cast<Feat *>(col + mcap);                                      // [mcap] features (32-bit metrics) or scaled colours
 
 	const int by = t / v.blocks_w, bx = t - by * v.blocks_w;
@@ -437,10 +527,10 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, uint32
 
 	// 4. colour pair scan
 	uint32_t cij;
-	if (kPack && m <= 128) // sums < 16 * 20681 < 2^19, at most 8128 pairs: (sum, rank) fits one word
-		cij = scan_tiles_keyed<19>(rows, m, lane, eight);
+	if constexpr (M::kMayBeNegative) // SRGB: sums can wrap negative, no lower bound to prune with
+		cij = scan_tiles<kPack, true, true>(rows, m, lane);
 	else
-		cij = scan_tiles<kPack, true, M::kMayBeNegative>(rows, m, lane);
+		cij = scan_pruned<kPack>(rows, q8, cneg, m, n, lane, sadj);
 	const uint32_t c0 = col[cij >> 16], c1 = col[cij & 0xFFFFu];
 	uint32_t a01 = 0;
 
@@ -460,7 +550,7 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, uint32
 		}
 		__syncwarp();
 		// alpha sums < 16 * 65025 < 2^20, up to 4095 pairs (m <= 90) for the keyed scan
-		const uint32_t aij = m <= 90 ? scan_tiles_keyed<20>(rows, m, lane, eight) : scan_tiles<true, false, false>(rows, m, lane);
+		const uint32_t aij = scan_pruned<true>(rows, q8, cneg, m, n, lane, sadj);
 		a01 = (col[aij >> 16] >> 24) | ((col[aij & 0xFFFFu] >> 24) << 8);
 	}
 	if (lane == 0)
@@ -490,7 +580,8 @@ static cudaError_t launch_search_cd(int nrandom, const ImageView &v, const uint1
 			return e;
 	}
 	const dim3 block(kSearchThreads), grid((nblocks + kSearchWarps - 1) / kSearchWarps);
-	kern<<<grid, block, smem, stream>>>(v, nrandom, mcap, wb, 8u, cand_c, cand_a, ends);
+	static const int sadj = [] { const char *e = getenv("S2TC_B200_SADJ"); return e ? atoi(e) : 0; }();
+	kern<<<grid, block, smem, stream>>>(v, nrandom, mcap, wb, sadj, cand_c, cand_a, ends);
 	return cudaGetLastError();
 }
 
