@@ -72,13 +72,6 @@ struct PendingTiming {
 };
 
 constexpr int kPlanRing = 64;
-constexpr int kBlocksPerRandThreadDefault = 8;
-static int rand_bpt()
-{
-	static const int v = [] { const char *e = getenv("S2TC_B200_RAND_BPT"); int n = e ? atoi(e) : 0; return n > 0 && n <= 4096 ? n : kBlocksPerRandThreadDefault; }();
-	return v;
-}
-#define kBlocksPerRandThread rand_bpt()
 constexpr long long kSlabBlocks = 1 << 22; // MODE_NORMAL works through an image in slabs of at most this many blocks
 
 } // namespace
@@ -87,7 +80,7 @@ struct s2tc_b200_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
 	std::mutex mu;
-	DevBuf src, reduced, out, ends, cand_c, cand_a, dither_ws, plans, small, mip, rand_ws;
+	DevBuf src, reduced, out, ends, dither_ws, plans, small, mip, rand_ws;
 	RandPlan *h_plans = nullptr; // pinned ring
 	int plan_next = 0;
 	int *h_carry = nullptr; // pinned, 4 ints
@@ -168,32 +161,28 @@ int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &
 	if (nrandom > pair_search_max_nrandom())
 		return fail(S2TC_B200_EUNSUPPORTED, "S2TC_RANDOM_COLORS=%d exceeds the %d candidates the search kernel can hold in shared memory",
 				nrandom, pair_search_max_nrandom());
-	if (nrandom) {
-		CU(c->cand_c.reserve((size_t) nblocks * nrandom * sizeof(uint16_t)));
-		if (s.dxt == kDxt5)
-			CU(c->cand_a.reserve((size_t) nblocks * nrandom));
-		// jump polynomials for this slab: thread t starts at cursor0 + (blk0 + 32 t) * draws_per_block
-		const uint64_t dpb = (uint64_t) draws_per_block(s.dxt, nrandom);
-		if (c->plan_next == kPlanRing) { // ring exhausted: wait for the copies queued so far
-			CU(cudaStreamSynchronize(st));
-			c->plan_next = 0;
-		}
-		RandPlan *hp = &c->h_plans[c->plan_next];
-		RandPlan *dp = (RandPlan *) c->plans.p + c->plan_next;
-		c->plan_next++;
-		rand_plan_init(*hp, cursor0 + (uint64_t) blk0 * dpb, (uint64_t) kBlocksPerRandThread * dpb);
-		const RandPlan *hp_dev = nullptr;
-		CU(cudaHostGetDevicePointer((void **) &hp_dev, hp, 0));
+	// jump polynomials for this slab: the warp that owns chunk t (kSearchChunkBlocks blocks) starts at
+	// cursor0 + (blk0 + kSearchChunkBlocks t) * draws_per_block
+	const uint64_t dpb = (uint64_t) draws_per_block(s.dxt, nrandom);
+	if (c->plan_next == kPlanRing) { // ring exhausted: wait for the uploads queued so far
+		CU(cudaStreamSynchronize(st));
+		c->plan_next = 0;
+	}
+	RandPlan *hp = &c->h_plans[c->plan_next];
+	RandPlan *dp = (RandPlan *) c->plans.p + c->plan_next;
+	c->plan_next++;
+	rand_plan_init(*hp, cursor0 + (uint64_t) blk0 * dpb, (uint64_t) kSearchChunkBlocks * dpb);
+	const RandPlan *hp_dev = nullptr;
+	CU(cudaHostGetDevicePointer((void **) &hp_dev, hp, 0));
+	CU(c->rand_ws.reserve(rand_windows_bytes((size_t) nblocks)));
+	{
+		FamScope f(c, st, kFamCand, 2);
 		CU(launch_plan_upload(hp_dev, dp, st));
-		CU(c->rand_ws.reserve(random_candidates_workspace_bytes((size_t) nblocks, kBlocksPerRandThread)));
-		FamScope f(c, st, kFamCand, 3);
-		CU(launch_random_candidates(s.dxt, nrandom, v, dp, kBlocksPerRandThread, (uint32_t *) c->rand_ws.p, (uint16_t *) c->cand_c.p,
-				(uint8_t *) c->cand_a.p, st));
+		CU(launch_rand_windows(dp, (unsigned) ((nblocks + kSearchChunkBlocks - 1) / kSearchChunkBlocks), (uint32_t *) c->rand_ws.p, st));
 	}
 	{
 		FamScope f(c, st, kFamSearch, 1);
-		CU(launch_pair_search(s.dxt, s.cd, nrandom, v, (const uint16_t *) c->cand_c.p, (const uint8_t *) c->cand_a.p,
-				(uint2 *) c->ends.p, st));
+		CU(launch_pair_search(s.dxt, s.cd, nrandom, v, (const uint32_t *) c->rand_ws.p, (uint2 *) c->ends.p, st));
 	}
 	{
 		FamScope f(c, st, kFamFinish, 1);
@@ -334,7 +323,7 @@ void s2tc_b200_ctx_destroy(s2tc_b200_ctx *c)
 		cudaEventDestroy(p.a);
 		cudaEventDestroy(p.b);
 	}
-	DevBuf *bufs[] = {&c->src, &c->reduced, &c->out, &c->ends, &c->cand_c, &c->cand_a, &c->dither_ws, &c->plans, &c->small, &c->mip, &c->rand_ws};
+	DevBuf *bufs[] = {&c->src, &c->reduced, &c->out, &c->ends, &c->dither_ws, &c->plans, &c->small, &c->mip, &c->rand_ws};
 	for (DevBuf *b : bufs)
 		b->release();
 	cudaFreeHost(c->h_plans);

@@ -118,19 +118,21 @@ inline cudaError_t init_all_luts(cudaStream_t stream)
 // MODE_FAST: candidates + refinement + packing in one pass, one thread per block.
 cudaError_t launch_fast_encode(int dxt, int cd, int refine, const ImageView &v, void *d_out, cudaStream_t stream);
 
-// MODE_NORMAL step 1 (nrandom > 0): random candidate colours for every block of the view.
-// d_cand_c: [blocks][nrandom] uint16 (565), d_cand_a: [blocks][nrandom] uint8 (DXT5 only)
-// d_windows: workspace of random_candidates_workspace_bytes(blocks, blocks_per_thread)
-size_t random_candidates_workspace_bytes(size_t nblocks, int blocks_per_thread);
+// MODE_NORMAL with random candidates (nrandom > 0): candidate generation + the c0/c1 (and DXT5 a0/a1) pair search, one warp
+// per chunk of kSearchChunkBlocks consecutive blocks (kernels_search.cu).
+// d_windows: the rand() window of every chunk at its first draw, [31][chunks] words, from launch_rand_windows with a plan
+// whose stride is kSearchChunkBlocks * draws_per_block.
+// d_ends: [blocks] uint2 {c0_565 | c1_565 << 16, a0 | a1 << 8}
+constexpr int kSearchChunkBlocks = 32;
+inline size_t rand_windows_bytes(size_t nblocks)
+{
+	return ((nblocks + kSearchChunkBlocks - 1) / kSearchChunkBlocks) * kLag * sizeof(uint32_t) + 256;
+}
 // plan: mapped pinned host memory -> device memory, by a kernel (no DMA engine involved)
 cudaError_t launch_plan_upload(const RandPlan *mapped_host_plan, RandPlan *d_plan, cudaStream_t stream);
-cudaError_t launch_random_candidates(int dxt, int nrandom, const ImageView &v, const RandPlan *d_plan,
-		int blocks_per_thread, uint32_t *d_windows, uint16_t *d_cand_c, uint8_t *d_cand_a, cudaStream_t stream);
-
-// MODE_NORMAL step 2: the c0/c1 (and DXT5 a0/a1) pair search, a thread group per block.
-// d_ends: [blocks] uint2 {c0_565 | c1_565 << 16, a0 | a1 << 8}
-cudaError_t launch_pair_search(int dxt, int cd, int nrandom, const ImageView &v, const uint16_t *d_cand_c,
-		const uint8_t *d_cand_a, uint2 *d_ends, cudaStream_t stream);
+cudaError_t launch_rand_windows(const RandPlan *d_plan, unsigned nsegments, uint32_t *d_windows, cudaStream_t stream);
+cudaError_t launch_pair_search(int dxt, int cd, int nrandom, const ImageView &v, const uint32_t *d_windows, uint2 *d_ends,
+		cudaStream_t stream);
 // largest nrandom the search kernel can hold in shared memory
 int pair_search_max_nrandom();
 

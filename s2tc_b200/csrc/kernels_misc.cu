@@ -742,42 +742,6 @@ __device__ __forceinline__ void poly_mulmod_regs(uint32_t (&a)[kLag], const uint
 		a[i] = t[i];
 }
 
-// x % len for x < 2^31 with the precomputed m = floor((2^32 - 1) / len): one multiply-high, one correction
-__device__ __forceinline__ int mod_small(uint32_t x, uint32_t len, uint32_t m)
-{
-	uint32_t r = x - __umulhi(x, m) * len;
-	if (r >= len)
-		r -= len;
-	return (int) r;
-}
-
-struct CandBoxFast {
-	int lo[4];
-	uint32_t len[4], rcp[4];
-};
-
-template <int DXT>
-__device__ __forceinline__ void box_of_block(const ImageView &v, int blk, CandBoxFast &bx)
-{
-	const int by = blk / v.blocks_w, bxx = blk - by * v.blocks_w;
-	Block b;
-	load_block(v, bxx, by, b);
-	uint32_t c[16];
-	uint8_t ca[16];
-	const int n = gather_colors<DXT>(b, c, ca);
-	const CandBox box = candidate_box(c, ca, n);
-#pragma unroll
-	for (int ch = 0; ch < 3; ++ch) {
-		bx.lo[ch] = box.lo[ch];
-		bx.len[ch] = (uint32_t) box.len[ch];
-	}
-	bx.lo[3] = box.alo;
-	bx.len[3] = (uint32_t) box.alen;
-#pragma unroll
-	for (int ch = 0; ch < 4; ++ch)
-		bx.rcp[ch] = 0xFFFFFFFFu / bx.len[ch];
-}
-
 // Step 1 of candidate generation: every generator thread's window of the rand() stream,
 // x^(cursor of its first block) = start * prod step[j]^(bit j of t), written as windows[slot][thread] (coalesced).
 // Kept apart from the generator loop because the polynomial products need ~120 registers and the loop ~60:
@@ -812,88 +776,6 @@ rand_windows_kernel(const RandPlan *__restrict__ plan, unsigned nthreads, uint32
 		windows[(size_t) s * nthreads + t] = w[s];
 }
 
-// Step 2.  31 candidates = 93 (DXT5: 124) draws = 3 (4) full turns of the 31-word generator ring, so inside this unit
-// the ring slot and the channel of every draw are compile-time constants and the ring lives in registers.
-template <int DXT>
-__global__ void __launch_bounds__(128, 4)
-random_candidates_kernel(ImageView v, int nrandom, const uint32_t *__restrict__ windows, unsigned nthreads, int blocks_per_thread,
-		uint16_t *__restrict__ cand_c, uint8_t *__restrict__ cand_a)
-{
-	constexpr int kDraws = DXT == kDxt5 ? 4 : 3; // per candidate: r, g, b [, a] (ref :986-990)
-	const int nblocks = v.blocks_w * v.blocks_h;
-	const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-	const long long b0 = (long long) t * blocks_per_thread;
-	if (t >= nthreads || b0 >= nblocks)
-		return;
-	const int b1 = (int) min((long long) nblocks, b0 + blocks_per_thread);
-	uint32_t w[kLag];
-#pragma unroll
-	for (int s = 0; s < kLag; ++s)
-		w[s] = __ldg(windows + (size_t) s * nthreads + t);
-
-	// A block's candidates are staged in this thread's line of shared memory and flushed with 128-bit stores when the
-	// block is complete: scattered 2-byte global stores (one 32-byte sector each) were what bounded the first version.
-	extern __shared__ __align__(16) uint8_t s_stage[];
-	const int pitch = ((2 * nrandom + 15) & ~15) + 16 * ((((2 * nrandom + 15) >> 4) & 1) ^ 1); // odd multiple of 16 B: conflict-free lines
-	uint16_t *line = reinterpret_cast<uint16_t *>(s_stage + (size_t) threadIdx.x * pitch);
-	uint8_t *aline = s_stage + (size_t) blockDim.x * pitch + (size_t) threadIdx.x * pitch;
-	auto flush = [&](int b) {
-		const size_t o = (size_t) b * nrandom;
-		if (((o * 2) & 15) == 0 && (nrandom & 7) == 0) {
-			uint4 *g = reinterpret_cast<uint4 *>(cand_c + o);
-			for (int q = 0; q < nrandom / 8; ++q)
-				g[q] = reinterpret_cast<const uint4 *>(line)[q];
-		} else {
-			for (int q = 0; q < nrandom; ++q)
-				cand_c[o + q] = line[q];
-		}
-		if (DXT == kDxt5) {
-			if ((o & 15) == 0 && (nrandom & 15) == 0) {
-				uint4 *g = reinterpret_cast<uint4 *>(cand_a + o);
-				for (int q = 0; q < nrandom / 16; ++q)
-					g[q] = reinterpret_cast<const uint4 *>(aline)[q];
-			} else {
-				for (int q = 0; q < nrandom; ++q)
-					cand_a[o + q] = aline[q];
-			}
-		}
-	};
-
-	int blk = (int) b0, k = 0;
-	CandBoxFast box;
-	box_of_block<DXT>(v, blk, box);
-	const long long total = (long long) (b1 - (int) b0) * nrandom; // candidates this thread owes
-	for (long long g0 = 0; g0 < total; g0 += kLag) {
-#pragma unroll
-		for (int c = 0; c < kLag; ++c) { // candidate c of the unit: draws kDraws*c .. kDraws*c + kDraws - 1
-			int comp[4] = {0, 0, 0, 0};
-#pragma unroll
-			for (int ch = 0; ch < kDraws; ++ch) {
-				const int slot = (kDraws * c + ch) % kLag;
-				const uint32_t val = w[slot] + w[(slot + 28) % kLag];
-				w[slot] = val;
-				comp[ch] = box.lo[ch] + mod_small(val >> 1, box.len[ch], box.rcp[ch]);
-			}
-			if (g0 + c < total) {
-				line[k] = (uint16_t) ((comp[0] << 11) | (comp[1] << 5) | comp[2]);
-				if (DXT == kDxt5)
-					aline[k] = (uint8_t) comp[3];
-				if (++k == nrandom) {
-					flush(blk);
-					k = 0;
-					if (++blk < b1)
-						box_of_block<DXT>(v, blk, box);
-				}
-			}
-		}
-	}
-}
-
-size_t random_candidates_workspace_bytes(size_t nblocks, int blocks_per_thread)
-{
-	return ((nblocks + blocks_per_thread - 1) / blocks_per_thread) * kLag * sizeof(uint32_t) + 256;
-}
-
 // Brings one jump-ahead plan (4.3 KB) from mapped pinned host memory into device memory.  A kernel, not a
 // cudaMemcpyAsync: on the compute stream a small host-to-device copy queues behind the slab uploads of the copy
 // stream in the DMA engine, and the first slab's kernels then start only when the whole image has been uploaded
@@ -911,39 +793,12 @@ cudaError_t launch_plan_upload(const RandPlan *mapped_host_plan, RandPlan *d_pla
 	return cudaGetLastError();
 }
 
-cudaError_t launch_random_candidates(int dxt, int nrandom, const ImageView &v, const RandPlan *d_plan,
-		int blocks_per_thread, uint32_t *d_windows, uint16_t *d_cand_c, uint8_t *d_cand_a, cudaStream_t stream)
+cudaError_t launch_rand_windows(const RandPlan *d_plan, unsigned nsegments, uint32_t *d_windows, cudaStream_t stream)
 {
-	const long long nblocks = (long long) v.blocks_w * v.blocks_h;
-	if (nblocks == 0 || nrandom <= 0)
+	if (nsegments == 0)
 		return cudaSuccess;
-	const unsigned threads = (unsigned) ((nblocks + blocks_per_thread - 1) / blocks_per_thread);
-	const dim3 block(128), grid((threads + 127) / 128);
-	rand_windows_kernel<<<grid, block, 0, stream>>>(d_plan, threads, d_windows);
-	const int pitch = ((2 * nrandom + 15) & ~15) + 16 * ((((2 * nrandom + 15) >> 4) & 1) ^ 1);
-	const size_t smem = (size_t) 128 * pitch * (dxt == kDxt5 ? 2 : 1);
-	cudaError_t e = cudaSuccess;
-	switch (dxt) {
-	case kDxt1:
-		if (smem > 48 * 1024)
-			e = cudaFuncSetAttribute(random_candidates_kernel<kDxt1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		if (e == cudaSuccess)
-			random_candidates_kernel<kDxt1><<<grid, block, smem, stream>>>(v, nrandom, d_windows, threads, blocks_per_thread, d_cand_c, d_cand_a);
-		break;
-	case kDxt3:
-		if (smem > 48 * 1024)
-			e = cudaFuncSetAttribute(random_candidates_kernel<kDxt3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		if (e == cudaSuccess)
-			random_candidates_kernel<kDxt3><<<grid, block, smem, stream>>>(v, nrandom, d_windows, threads, blocks_per_thread, d_cand_c, d_cand_a);
-		break;
-	default:
-		if (smem > 48 * 1024)
-			e = cudaFuncSetAttribute(random_candidates_kernel<kDxt5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		if (e == cudaSuccess)
-			random_candidates_kernel<kDxt5><<<grid, block, smem, stream>>>(v, nrandom, d_windows, threads, blocks_per_thread, d_cand_c, d_cand_a);
-		break;
-	}
-	return e != cudaSuccess ? e : cudaGetLastError();
+	rand_windows_kernel<<<(nsegments + 127) / 128, 128, 0, stream>>>(d_plan, nsegments, d_windows);
+	return cudaGetLastError();
 }
 
 // =====================================================================================================

@@ -1,29 +1,26 @@
-// kernels_search.cu -- MODE_NORMAL with random candidates (S2TC_RANDOM_COLORS > 0): the c0/c1 pair search
-// (reference reduce_colors_inplace and reduce_colors_inplace_2fixpoints, s2tc_algorithm.cpp:367-478, reached
-// from :1004-1006), one warp per 4x4 block.
+// kernels_search.cu -- MODE_NORMAL with random candidates (S2TC_RANDOM_COLORS > 0): candidate generation and the
+// c0/c1 pair search (reference s2tc_algorithm.cpp:962-993, reduce_colors_inplace and reduce_colors_inplace_2fixpoints
+// :367-478, reached from :1004-1006).  One warp owns a chunk of 32 consecutive 4x4 blocks and works through them.
 //
-// Per block the reference builds dists[m][n] (m = n gathered colours + nrandom random candidates, n <= 16) and
-// scans all m(m-1)/2 pairs for the smallest sum_k min(d[i][k], d[j][k]): 3160 pairs x 16 texels at
-// nrandom = 64, >90 % of its run time.  Here:
-//   * the warp gathers the block's colours, appends the pre-generated random candidates and fills the
-//     distance matrix in shared memory, one row per candidate, columns zero-padded to 16;
-//   * metrics whose distances fit 15 bits (AVG, WAVG, W0AVG <= 20681) and alpha (<= 65025) are stored as
-//     16-bit halves: a row is 8 words, a pair costs 8 VIMNMX.U16x2 and the 16-term sum is formed with
-//     packed three-operand adds (3 x 20681 < 2^16) and three IDP.2A horizontal adds; the other metrics keep
-//     32-bit rows (16 VIMNMX + IADD3 tree);
-//   * the pair triangle is walked in 16x16 tiles: lane (jj, half) keeps row j = 16b+jj of tile column b in
-//     registers and meets rows i = 16a + 8*half + t, t = 0..7, whose loads are warp broadcasts (two distinct
-//     addresses per LDS.128), so shared-memory traffic is ~2 wavefronts per 32 pairs; row pitches (12 / 20
-//     words) make the per-lane row loads conflict-free;
-//   * every lane keeps its minimum by (sum, i, j) and the warp merges lexicographically, which is the
-//     reference's "first minimum in (i, j) order";
-//   * when a sum went negative (only the SRGB metric can wrap) lane 0 replays the reference's
-//     acceptance rule "bestsum < 0 || sum < bestsum" verbatim over the stored matrix;
-//   * DXT5 repeats the search for alpha, the two fixed points 0 and 255 folded into every row
-//     (min(d[i][k], f[k]) is stored, so the pair loop is unchanged).
-// Output: the chosen endpoints, 8 bytes per block; kernels_finish.cu turns them into DXT blocks.
-// History: the first version (32-bit rows, lanes striding j with 70 % utilisation) took 198 ms for the
-// 16.7 M blocks of config 3 (profiles/r01c).
+// Per block the reference builds dists[m][n] (m = n gathered colours + nrandom random candidates, n <= 16) and scans all
+// m(m-1)/2 pairs for the smallest sum_k min(d[i][k], d[j][k]): 3160 pairs x 16 texels at nrandom = 64, > 90 % of its
+// run time.  Here, per block:
+//   1. gather (one ballot), bounding box (warp reductions);  a block whose gathered colours are all equal has an all-zero
+//      matrix and the reference keeps pair (0, 1): answered at once;
+//   2. the random candidates come straight from the warp's own copy of glibc's rand() state: lane l holds word l of the
+//      31-word window, and the recurrence q[i+31] = q[i] + q[i+28] yields the next 31 values as prefix sums along the
+//      three stride-3 chains of the window (shuffle steps).  A chunk's window at its first draw is computed by
+//      rand_windows_kernel (polynomial jump-ahead, glibc_rand.cuh); a block always consumes 3 (DXT5: 4) x nrandom draws;
+//   3. the exact distance matrix in shared memory, one row per candidate: 16-bit halves for the metrics that fit
+//      (AVG, WAVG, W0AVG <= 20681; alpha <= 65025), 32-bit rows otherwise;
+//   4. the PRUNED pair scan (below): a 4-instruction lower bound per pair, exact sums only for the pairs that survive it;
+//   5. DXT5 repeats 3-4 for alpha with the two fixed points 0 and 255 folded into every row (min(d[i][k], f[k]) is
+//      stored, so the pair scan is unchanged).
+// Output: the chosen endpoints, 8 bytes per block, written once per chunk; kernels_finish.cu turns them into DXT blocks.
+//
+// History of this kernel on config 3 (16.7 M DXT1 blocks, WAVG, nrandom = 64): 198 ms (32-bit rows) -> 52.1 ms (round 1:
+// exact scan in 16x16 tiles, 8 VIMNMX.U16x2 + 8 IDP.2A per pair, 90 % issue utilisation, + 5.3 ms for a separate
+// candidate kernel) -> this version.
 #define S2TC_USE_SRGB_MIXED_LUT
 #include "kernels.cuh"
 
@@ -31,22 +28,44 @@ namespace s2tc {
 
 constexpr int kSearchThreads = 128;
 constexpr int kSearchWarps = kSearchThreads / 32;
-constexpr int kPitch16 = 12; // words per row, 16-bit distances (8 used): 8 consecutive rows -> 8 distinct 16-byte slots
+constexpr int kPitch16 = 8;  // words per row, 16-bit distances: rows are only read whole (quantisation, exact sums of survivors)
 constexpr int kPitch32 = 20; // words per row, 32-bit distances (16 used)
+constexpr int kListCap = 288; // survivors waiting for their exact sum: < 32 carried over + at most 256 from one tile
+constexpr int kRing = 256;    // rand() outputs kept per warp (a batch of 32 candidates needs <= 128 + 61)
 
 template <int CD> struct Packs16 { static constexpr bool value = CD == kAVG || CD == kWAVG || CD == kW0AVG; };
 
-// per-warp shared memory: texels [16] | exact rows [(mcap+16)][pitch] | quantised rows [(mcap+16)] x 16 B | c [(mcap+16)] |
-// colours [mcap] | features [mcap]
-__host__ __device__ inline size_t search_warp_bytes(int mcap, bool pack16, bool has_feat)
+// per-warp shared memory, byte offsets (all multiples of 16).  Two regions are used twice: the rand() ring lives where the
+// distance rows will be (candidates are drawn before the matrix is filled), the survivor list where the metric features
+// were (the scan starts after the fill).
+struct WarpLayout {
+	int rows_cap; // matrix rows: m rounded up to whole 16-row tiles
+	uint32_t texels, rows, q8, cneg, col, feat, misc, total;
+};
+__host__ __device__ inline WarpLayout warp_layout(int mcap, bool pack16)
 {
-	const size_t rows = (size_t) (mcap + 16) * (pack16 ? kPitch16 : kPitch32) * 4; // +16: tile loads may touch one tile past m
-	size_t b = 64 + rows + (size_t) (mcap + 16) * 20 + (size_t) mcap * 4 + (has_feat ? (size_t) mcap * 12 : 0);
-	return (b + 15) & ~(size_t) 15;
+	WarpLayout L;
+	L.rows_cap = (mcap + 15) & ~15;
+	uint32_t o = 0;
+	L.texels = o; o += 64;                                                       // the current block's texels, reduced
+	uint32_t rows = (uint32_t) L.rows_cap * (pack16 ? kPitch16 : kPitch32) * 4;
+	if (rows < kRing * 4)
+		rows = kRing * 4;
+	L.rows = o; o += rows;                                                       // exact distance rows | rand() ring
+	L.q8 = o; o += (uint32_t) L.rows_cap * 16;                                   // quantised rows, one byte per texel
+	L.cneg = o; o += (uint32_t) L.rows_cap * 4;                                  // K - row sum of the quantised row
+	L.col = o; o += ((uint32_t) mcap * 4 + 15) & ~15u;                           // candidate colours
+	uint32_t feat = ((uint32_t) mcap * (pack16 ? 8 : 12) + 15) & ~15u;
+	if (feat < kListCap * 4)
+		feat = kListCap * 4;
+	L.feat = o; o += feat;                                                       // metric features | survivor list
+	L.misc = o; o += 16;
+	L.total = o;
+	return L;
 }
 
-// one texel row of a block as reduced texels (zeros outside the image)
-__device__ __forceinline__ void load_block_row(const ImageView &v, int x0, int y, int w, uint32_t t[4])
+// one texel row of a block as reduced texels (zeros outside the image); every index a compile-time constant
+__device__ __forceinline__ void load_block_row(const ImageView &v, int x0, int y, int w, uint32_t (&t)[4])
 {
 	t[0] = t[1] = t[2] = t[3] = 0;
 	if (y >= v.rows)
@@ -58,22 +77,26 @@ __device__ __forceinline__ void load_block_row(const ImageView &v, int x0, int y
 			const uint4 q = __ldg(reinterpret_cast<const uint4 *>(row));
 			t[0] = q.x; t[1] = q.y; t[2] = q.z; t[3] = q.w;
 		} else {
-			for (int x = 0; x < w; ++x)
-				t[x] = __ldg(reinterpret_cast<const uint32_t *>(row) + x);
-		}
-		if (v.fmt == kSrcRGBA8)
+#pragma unroll
 			for (int x = 0; x < 4; ++x)
-				t[x] = reduce_word(t[x], v.alphabits);
-		for (int x = w; x < 4; ++x)
-			t[x] = 0;
+				if (x < w)
+					t[x] = __ldg(reinterpret_cast<const uint32_t *>(row) + x);
+		}
+		if (v.fmt == kSrcRGBA8) {
+#pragma unroll
+			for (int x = 0; x < 4; ++x)
+				t[x] = x < w ? reduce_word(t[x], v.alphabits) : 0u;
+		}
 	} else {
 		const size_t pitch = (size_t) v.width * 3;
 		const uint8_t *row = v.base + (size_t) y * pitch + (size_t) x0 * 3;
 		const uint32_t ones = ((1u << v.alphabits) - 1u) << 24;
-		for (int x = 0; x < w; ++x) {
-			const uint8_t *q = row + x * 3;
-			t[x] = (uint32_t) (__ldg(q) >> 3) | ((uint32_t) (__ldg(q + 1) >> 2) << 8) | ((uint32_t) (__ldg(q + 2) >> 3) << 16) | ones;
-		}
+#pragma unroll
+		for (int x = 0; x < 4; ++x)
+			if (x < w) {
+				const uint8_t *q = row + x * 3;
+				t[x] = (uint32_t) (__ldg(q) >> 3) | ((uint32_t) (__ldg(q + 1) >> 2) << 8) | ((uint32_t) (__ldg(q + 2) >> 3) << 16) | ones;
+			}
 	}
 }
 
@@ -130,44 +153,26 @@ template <> struct RowRegs<false> {
 	}
 };
 
-// rank of pair (i, j), i < j < m, in the reference's lexicographic scan order
-__device__ __forceinline__ int pair_rank(int i, int j, int m) { return i * m - ((i * (i + 1)) >> 1) + (j - i - 1); }
-
-// pair number p (lexicographic over i < j < 16) -> i | j << 8, padded to 128 entries
-struct DiagPairs {
-	uint16_t v[128];
-	constexpr DiagPairs() : v()
-	{
-		int p = 0;
-		for (int i = 0; i < 16; ++i)
-			for (int j = i + 1; j < 16; ++j)
-				v[p++] = (uint16_t) (i | (j << 8));
-		for (; p < 128; ++p)
-			v[p] = (uint16_t) (0 | (1 << 8));
-	}
-};
-__device__ const DiagPairs kDiagPairs{};
-
 // ---- pruned scan ---------------------------------------------------------------------------------------
 // The exact pair scan costs 16 min + 16 add per pair.  Most pairs are nowhere near the minimum, and a cheap LOWER
 // BOUND of a pair's sum shows it:  with q[i][k] = min(255, d[i][k] >> s)  (one byte per texel, 16 bytes per row)
 //     sum_k min(d[i][k], d[j][k])  >=  2^s * sum_k min(q[i][k], q[j][k])  =  2^s * (Rq[i] + Rq[j] - SAD(q[i], q[j])) / 2,
 // Rq = row sums, SAD = sum of absolute byte differences: four VABSDIFF4.U8.ACC per pair, 16 texels in 4 instructions.
 // A pair can only beat (or tie) the best exact sum T found so far if its bound is <= T; everything else is skipped
-// without ever being evaluated exactly.  The result is the reference's: every pair whose exact sum could be the
-// first minimum in (i, j) order is evaluated exactly and compared by (sum, rank).
-//   0. the 120 pairs of the first diagonal tile (the block's own colours) are scanned exactly: T, and from T the
-//      shift s (values above T never matter, so 8 bits cover [0, T] as finely as they can);
+// without ever being evaluated exactly.  The result is the reference's: every pair whose exact sum could be the first
+// minimum in (i, j) order is evaluated exactly and compared by (sum, i, j).
+//   0. 32 sample pairs among the first 16 rows (the block's own colours) are evaluated exactly: a first T, and from T
+//      the shift s (values above T never matter, so 8 bits cover [0, T] as finely as they can);
 //   1. every lane quantises rows: q bytes and c[i] = K - Rq[i];
-//   2. 16x16 tiles as before: lane (jj, half) keeps the q rows j of up to four tile columns in registers and meets the
-//      eight rows i = 16a + 8 half + t (broadcast loads).  acc = c[i] + SAD(q[i], q[j]) = K + Rq[j] - 2 bound, so the pair
-//      survives iff acc >= K + Rq[j] - 2 (T >> s), a per-lane constant: the loop only keeps max_t acc (VIMNMX3);
-//   3. after each group of tiles the (rare) lanes whose maximum passes walk their eight rows again, evaluate the
-//      surviving pairs exactly from the full-precision rows and the warp agrees on the new (T, rank).
-// Diagonal tiles go through the same loop (slots with i >= j only raise false alarms that step 3 discards); rows
+//   2. 16x16 tiles: lane (jj, half) keeps the q row j = 16b + jj in registers and meets the eight rows i = 16a + 8 half + t
+//      (broadcast loads).  acc = c[i] + SAD(q[i], q[j]) = K + Rq[j] - 2 bound, so the pair survives iff
+//      acc >= K + Rq[j] - 2 (T >> s), a per-lane constant: one test per four pairs on their maximum;
+//   3. survivors (rare) are appended to a list; when 32 are waiting, or at the end of a tile column, the warp evaluates
+//      them exactly, one per lane, from the full-precision rows and agrees on the new (T, i, j).
+// Diagonal tiles go through the same loop (slots with i >= j are discarded when they try to enter the list); rows
 // beyond m are all-255 (bound = Rq[i], never better than a real pair of row i).
 // Measured on a B200 (tools_lab/ubench_sad.cu): VABSDIFF4 issues every other clock per scheduler on the ALU pipe,
-// so the bound costs ~9 clocks per pair against ~21 for the exact form.
+// so the bound costs ~10 clocks per pair against ~21 for the exact form, and the other pipes stay free for the rest.
 constexpr uint32_t kBoundBias = 4096; // K > 16 * 255
 
 __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c)
@@ -176,16 +181,9 @@ __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c)
 	asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
 	return d;
 }
-template <int NW> __device__ __forceinline__ uint32_t sad_row(const uint4 &a, const uint4 &b, uint32_t c)
+__device__ __forceinline__ uint32_t sad_row(const uint4 &a, const uint4 &b, uint32_t c)
 {
-	c = sad4(a.x, b.x, c);
-	if (NW > 1)
-		c = sad4(a.y, b.y, c);
-	if (NW > 2)
-		c = sad4(a.z, b.z, c);
-	if (NW > 3)
-		c = sad4(a.w, b.w, c);
-	return c;
+	return sad4(a.w, b.w, sad4(a.z, b.z, sad4(a.y, b.y, sad4(a.x, b.x, c))));
 }
 
 // exact sum_k min(d[i][k], d[j][k]) from the full-precision rows
@@ -205,153 +203,140 @@ template <bool PACK16> __device__ __forceinline__ uint32_t exact_pair_sum(const 
 	}
 }
 
-struct BestPair { // lexicographic (sum, rank): the reference's first minimum
-	uint32_t sum, rank;
-	__device__ __forceinline__ void take(uint32_t s, uint32_t r)
+struct BestPair { // lexicographic (sum, i << 16 | j): the reference's first minimum
+	uint32_t sum, ij;
+	__device__ __forceinline__ void take(uint32_t s, uint32_t p)
 	{
-		if (s < sum || (s == sum && r < rank)) {
+		if (s < sum || (s == sum && p < ij)) {
 			sum = s;
-			rank = r;
+			ij = p;
 		}
 	}
-	__device__ __forceinline__ void warp_min()
+	__device__ __forceinline__ void warp_min() // two REDUX: the smallest sum, then the first pair that has it
 	{
-#pragma unroll
-		for (int off = 16; off > 0; off >>= 1) {
-			const uint32_t os = __shfl_xor_sync(0xFFFFFFFFu, sum, off), orank = __shfl_xor_sync(0xFFFFFFFFu, rank, off);
-			take(os, orank);
-		}
+		const uint32_t smin = __reduce_min_sync(0xFFFFFFFFu, sum);
+		ij = __reduce_min_sync(0xFFFFFFFFu, sum == smin ? ij : 0xFFFFFFFFu);
+		sum = smin;
 	}
 };
 
-// rows q of one lane for NC tile columns against the eight rows i0 .. i0+7: per-column maximum of acc
-template <int NW, int NC>
-__device__ __forceinline__ void bound_tile(const uint4 *q8, const uint32_t *cneg, int i0, const uint4 (&rj)[4], uint32_t (&mx)[4])
-{
-#pragma unroll
-	for (int c = 0; c < 4; ++c)
-		mx[c] = 0;
-#pragma unroll 4
-	for (int t = 0; t < 8; t += 2) {
-		const uint4 qa = q8[i0 + t], qb = q8[i0 + t + 1];
-		const uint32_t ca = cneg[i0 + t], cb = cneg[i0 + t + 1];
-#pragma unroll
-		for (int c = 0; c < NC; ++c) {
-			const uint32_t x = sad_row<NW>(qa, rj[c], ca), y = sad_row<NW>(qb, rj[c], cb);
-			mx[c] = max(mx[c], max(x, y));
-		}
-	}
-}
+// 32 pairs i < j < 16 spread over the 120 of the first tile, (0, 1) first
+__device__ const uint32_t kSamplePairs[32] = {0x00001u, 0x00004u, 0x00008u, 0x0000Cu, 0x10002u, 0x10006u, 0x1000Au, 0x1000Du,
+		0x20004u, 0x20008u, 0x2000Cu, 0x30004u, 0x30008u, 0x3000Bu, 0x3000Fu, 0x40008u, 0x4000Cu, 0x50006u, 0x5000Au, 0x5000Du, 0x60008u,
+		0x6000Cu, 0x70008u, 0x7000Cu, 0x80009u, 0x8000Cu, 0x9000Au, 0x9000Eu, 0xA000Du, 0xB000Du, 0xC000Eu, 0xE000Fu};
 
 // Returns (i << 16) | j of the winner in every lane.  rows: exact distance rows (16-bit packed, pitch kPitch16, or 32-bit,
-// pitch kPitch32; all values >= 0); q8 / cneg: workspace for 16 * ntile quantised rows.  n: columns in use.
+// pitch kPitch32; all values >= 0, columns >= n zero); q8 / cneg: workspace for 16 * ntile quantised rows; list: kListCap
+// words; cnt: one word, zero on entry and on exit.
 template <bool PACK16>
-__device__ __forceinline__ uint32_t scan_pruned(const uint32_t *rows, uint4 *q8, uint32_t *cneg, int m, int n, int lane, int sadj)
+__device__ __forceinline__ uint32_t pruned_search(const uint32_t *rows, uint4 *q8, uint32_t *cneg, uint32_t *list, uint32_t *cnt,
+		int m, int lane, int sadj)
 {
 	const int ntile = (m + 15) >> 4;
 	const int jj = lane & 15, half = lane >> 4;
-	// 0. first diagonal tile, exactly
 	BestPair best{0xFFFFFFFFu, 0xFFFFFFFFu};
-#pragma unroll
-	for (int q = 0; q < 4; ++q) {
-		const uint32_t ij = __ldg(&kDiagPairs.v[lane + 32 * q]);
-		const int i = (int) (ij & 0xFFu), j = (int) (ij >> 8);
-		if ((q < 3 || lane < 24) && j < m)
-			best.take(exact_pair_sum<PACK16>(rows, i, j), (uint32_t) pair_rank(i, j, m));
+	{ // 0. sample pairs
+		const uint32_t p = kSamplePairs[lane];
+		const int i = (int) (p >> 16), j = (int) (p & 0xFFFFu);
+		if (j < m)
+			best.take(exact_pair_sum<PACK16>(rows, i, j), p);
+		best.warp_min();
 	}
-	best.warp_min();
-	if (best.sum != 0 || best.rank != 0) { // pair (0, 1) with sum 0 cannot be beaten
-		// 1. quantise
-		const int s = max(0, 32 - __clz(best.sum) - 8 + sadj);
-		for (int r = lane; r < 16 * ntile; r += 32) {
-			uint4 q = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-			if (r < m) {
-				uint32_t h[8];
-				if constexpr (PACK16) {
-					RowRegs<true> rr;
-					rr.load(rows, r);
+	if (best.sum == 0 && best.ij == 1u) // pair (0, 1) with sum 0 cannot be beaten
+		return 1u;
+	// 1. quantise
+	const int s = max(0, 32 - __clz(best.sum) - 8 + sadj);
+	for (int r = lane; r < 16 * ntile; r += 32) {
+		uint4 q = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+		if (r < m) {
+			uint32_t h[8];
+			if constexpr (PACK16) {
+				RowRegs<true> rr;
+				rr.load(rows, r);
+				if (s == 0) {
+#pragma unroll
+					for (int w = 0; w < 8; ++w)
+						h[w] = __vminu2(rr.w[w], 0x00FF00FFu);
+				} else {
 					const uint32_t mask = (0xFFFFu >> s) * 0x10001u;
 #pragma unroll
 					for (int w = 0; w < 8; ++w)
 						h[w] = __vminu2((rr.w[w] >> s) & mask, 0x00FF00FFu);
-				} else {
-					RowRegs<false> rr;
-					rr.load(rows, r);
-#pragma unroll
-					for (int w = 0; w < 8; ++w)
-						h[w] = min((uint32_t) rr.w[2 * w] >> s, 255u) | (min((uint32_t) rr.w[2 * w + 1] >> s, 255u) << 16);
 				}
-				q.x = __byte_perm(h[0], h[1], 0x6420);
-				q.y = __byte_perm(h[2], h[3], 0x6420);
-				q.z = __byte_perm(h[4], h[5], 0x6420);
-				q.w = __byte_perm(h[6], h[7], 0x6420);
+			} else {
+				RowRegs<false> rr;
+				rr.load(rows, r);
+#pragma unroll
+				for (int w = 0; w < 8; ++w)
+					h[w] = min((uint32_t) rr.w[2 * w] >> s, 255u) | (min((uint32_t) rr.w[2 * w + 1] >> s, 255u) << 16);
 			}
-			q8[r] = q;
-			cneg[r] = kBoundBias - sad4(q.w, 0u, sad4(q.z, 0u, sad4(q.y, 0u, sad4(q.x, 0u, 0u))));
+			q.x = __byte_perm(h[0], h[1], 0x6420);
+			q.y = __byte_perm(h[2], h[3], 0x6420);
+			q.z = __byte_perm(h[4], h[5], 0x6420);
+			q.w = __byte_perm(h[6], h[7], 0x6420);
 		}
-		__syncwarp();
-		// 2./3. bound scan with exact evaluation of the survivors
-		const int nw = (n + 3) >> 2;
-		uint32_t tq2 = (best.sum >> s) * 2u;
-		for (int a = 0; a < ntile; ++a) {
+		q8[r] = q;
+		cneg[r] = kBoundBias - sad_row(q, make_uint4(0u, 0u, 0u, 0u), 0u);
+	}
+	__syncwarp();
+	// 2./3. bound scan; survivors to the list, exact evaluation in batches
+	uint32_t tq2 = (best.sum >> s) * 2u;
+	bool pending = false; // this lane has appended since the list was last emptied
+	for (int b = 0; b < ntile; ++b) {
+		const int j = 16 * b + jj;
+		const uint4 rj = q8[j];
+		const uint32_t rqk = 2u * kBoundBias - cneg[j]; // K + Rq[j]
+		const bool jok = j < m;
+		for (int a = 0; a <= b; ++a) {
 			const int i0 = 16 * a + 8 * half;
-			for (int b0 = a ? a : 1; b0 < ntile; b0 += 4) {
-				const int nc = min(4, ntile - b0);
-				uint4 rj[4];
-				uint32_t rq[4], mx[4];
+			const int thr = (int) (rqk - tq2); // survives iff acc >= K + Rq[j] - 2 (T >> s); may be negative
+			const uint4 *qi = q8 + i0;
+			const uint4 ca = *reinterpret_cast<const uint4 *>(cneg + i0), cb = *reinterpret_cast<const uint4 *>(cneg + i0 + 4);
+			uint32_t acc[8];
+			acc[0] = sad_row(qi[0], rj, ca.x);
+			acc[1] = sad_row(qi[1], rj, ca.y);
+			acc[2] = sad_row(qi[2], rj, ca.z);
+			acc[3] = sad_row(qi[3], rj, ca.w);
+			acc[4] = sad_row(qi[4], rj, cb.x);
+			acc[5] = sad_row(qi[5], rj, cb.y);
+			acc[6] = sad_row(qi[6], rj, cb.z);
+			acc[7] = sad_row(qi[7], rj, cb.w);
 #pragma unroll
-				for (int c = 0; c < 4; ++c) {
-					const int j = 16 * (b0 + (c < nc ? c : 0)) + jj;
-					rj[c] = q8[j];
-					rq[c] = 2u * kBoundBias - cneg[j]; // K + Rq[j]
-				}
-				switch ((nw - 1) * 4 + nc - 1) {
-#define S2TC_BT(NW, NC) case (NW - 1) * 4 + NC - 1: bound_tile<NW, NC>(q8, cneg, i0, rj, mx); break;
-				S2TC_BT(1, 1) S2TC_BT(1, 2) S2TC_BT(1, 3) S2TC_BT(1, 4)
-				S2TC_BT(2, 1) S2TC_BT(2, 2) S2TC_BT(2, 3) S2TC_BT(2, 4)
-				S2TC_BT(3, 1) S2TC_BT(3, 2) S2TC_BT(3, 3) S2TC_BT(3, 4)
-				S2TC_BT(4, 1) S2TC_BT(4, 2) S2TC_BT(4, 3) default: bound_tile<4, 4>(q8, cneg, i0, rj, mx); break;
-#undef S2TC_BT
-				}
-				bool hit = false;
+			for (int g = 0; g < 8; g += 4) {
+				const uint32_t top = max(max(acc[g], acc[g + 1]), max(acc[g + 2], acc[g + 3]));
+				if ((int) top >= thr && jok) {
 #pragma unroll
-				for (int c = 0; c < 4; ++c) {
-					// survives iff acc >= K + Rq[j] - 2 (T >> s); signed: the right-hand side may be negative
-					const bool f = c < nc && (int) mx[c] >= (int) (rq[c] - tq2);
-					if (__any_sync(0xFFFFFFFFu, f)) {
-						hit = true;
-						if (f) {
-							const int j = 16 * (b0 + c) + jj;
-							const int thr = (int) (rq[c] - tq2);
-							for (int t = 0; t < 8; ++t) {
-								const int i = i0 + t;
-								const uint32_t acc = sad_row<4>(q8[i], rj[c], cneg[i]);
-								if ((int) acc >= thr && i < j && j < m)
-									best.take(exact_pair_sum<PACK16>(rows, i, j), (uint32_t) pair_rank(i, j, m));
-							}
+					for (int t = g; t < g + 4; ++t)
+						if ((int) acc[t] >= thr && i0 + t < j) {
+							list[atomicAdd(cnt, 1u)] = ((uint32_t) (i0 + t) << 16) | (uint32_t) j;
+							pending = true;
 						}
-					}
 				}
-				if (hit) {
+			}
+			if (__any_sync(0xFFFFFFFFu, pending)) {
+				__syncwarp();
+				const uint32_t c = *cnt;
+				if (c >= 32u || a == b) {
+					__syncwarp(); // every lane has read the count
+					if (lane == 0)
+						*cnt = 0;
+					for (uint32_t idx = lane; idx < c; idx += 32) {
+						const uint32_t p = list[idx];
+						best.take(exact_pair_sum<PACK16>(rows, (int) (p >> 16), (int) (p & 0xFFFFu)), p);
+					}
 					best.warp_min();
 					tq2 = (best.sum >> s) * 2u;
+					pending = false;
+					__syncwarp(); // list consumed and count reset before anyone appends again
 				}
 			}
 		}
 	}
-	// rank -> (i, j): row i of the pair order starts at rank i (m - 1) - i (i - 1) / 2; every lane tests its rows and the
-	// one that holds the rank announces itself
-	const int rank = (int) best.rank;
-	uint32_t mine = 0;
-	for (int i = lane; i < m - 1; i += 32) {
-		const int start = i * (m - 1) - ((i * (i - 1)) >> 1);
-		if (rank >= start && rank < start + (m - 1 - i))
-			mine = ((uint32_t) i << 16) | (uint32_t) (i + 1 + rank - start);
-	}
-	return __reduce_or_sync(0xFFFFFFFFu, mine);
+	__syncwarp();
+	return best.ij;
 }
 
-// Generic scan: any row width, any sum range.  Returns (i << 16) | j of the winner in every lane.
+// Generic scan: any row width, any sum range, sums may wrap negative (SRGB).  Returns (i << 16) | j of the winner in every lane.
 template <bool PACK16, bool SUM3, bool MAY_BE_NEGATIVE>
 __device__ __forceinline__ uint32_t scan_tiles(const uint32_t *rows, int m, int lane)
 {
@@ -363,7 +348,7 @@ __device__ __forceinline__ uint32_t scan_tiles(const uint32_t *rows, int m, int 
 	for (int b = 0; b < ntile; ++b) {
 		const int j = 16 * b + jj;
 		RowRegs<PACK16> rj;
-		rj.load(rows, j); // rows beyond m are inside the allocation (padding tile) and never accepted
+		rj.load(rows, j); // rows beyond m are inside the allocation and never accepted
 		for (int a = 0; a <= b; ++a) {
 			const int i0 = 16 * a + 8 * half;
 #pragma unroll 4
@@ -419,169 +404,282 @@ __device__ __forceinline__ uint32_t scan_tiles(const uint32_t *rows, int m, int 
 	return bij;
 }
 
+// ---- the warp's rand() stream ------------------------------------------------------------------------------
+// floor((2^32 - 1) / len) for len = 1 .. 256 (filled at compile time)
+struct RcpTable {
+	uint32_t v[257];
+	constexpr RcpTable() : v()
+	{
+		v[0] = 0;
+		for (uint32_t i = 1; i <= 256; ++i)
+			v[i] = 0xFFFFFFFFu / i;
+	}
+};
+__device__ const RcpTable kRcp{};
+
+// x % len for x < 2^31 with rcp = floor((2^32 - 1) / len): one multiply-high, one correction
+__device__ __forceinline__ uint32_t mod_small(uint32_t x, uint32_t len, uint32_t rcp)
+{
+	uint32_t r = x - __umulhi(x, rcp) * len;
+	if (r >= len)
+		r -= len;
+	return r;
+}
+
+// win: word `lane` of the window q[e .. e+30] (lane 31 unused).  Advances the window by 31 positions and returns the lane's
+// new word q[e+31+lane]; the rand() outputs are these words >> 1 in lane order (glibc_rand.cuh: GlibcRand::next).
+//   new[l] = w[l] + new[l-3] (l >= 3),  new[l] = w[l] + w[28+l] (l < 3)   ==>   prefix sums along the stride-3 chains
+// one: the integer 1 as a kernel argument, so that "x += t if lane >= off" stays one IMAD (t * flag + x) on the FMA pipe
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c)
+{
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+struct RandLane {
+	uint32_t f0, f3, f6, f12, f24; // 1 where the lane takes part in the step, else 0
+	int src0;
+	__device__ __forceinline__ RandLane(int lane, uint32_t one)
+	{
+		f0 = lane < 3 ? one : 0u;
+		f3 = lane >= 3 ? one : 0u;
+		f6 = lane >= 6 ? one : 0u;
+		f12 = lane >= 12 ? one : 0u;
+		f24 = lane >= 24 ? one : 0u;
+		src0 = (lane + 28) & 31;
+	}
+	__device__ __forceinline__ uint32_t step31(uint32_t win) const
+	{
+		uint32_t x = mad_u32(__shfl_sync(0xFFFFFFFFu, win, src0), f0, win);
+		x = mad_u32(__shfl_up_sync(0xFFFFFFFFu, x, 3), f3, x);
+		x = mad_u32(__shfl_up_sync(0xFFFFFFFFu, x, 6), f6, x);
+		x = mad_u32(__shfl_up_sync(0xFFFFFFFFu, x, 12), f12, x);
+		x = mad_u32(__shfl_up_sync(0xFFFFFFFFu, x, 24), f24, x);
+		return x;
+	}
+};
+
 template <int DXT, int CD>
-__global__ void __launch_bounds__(kSearchThreads)
-pair_search_kernel(ImageView v, int nrandom, int mcap, size_t warp_bytes, int sadj, const uint16_t *__restrict__ cand_c,
-		const uint8_t *__restrict__ cand_a, uint2 *__restrict__ ends)
+__global__ void __launch_bounds__(kSearchThreads, 7)
+pair_search_kernel(ImageView v, int nrandom, int mcap, int sadj, uint32_t one, const uint32_t *__restrict__ windows, unsigned nchunks,
+		uint2 *__restrict__ ends)
 {
 	typedef Metric<CD> M;
 	typedef typename M::Feat Feat;
 	constexpr bool kPack = Packs16<CD>::value;
 	constexpr int kPitch = kPack ? kPitch16 : kPitch32;
+	constexpr int kDraws = DXT == kDxt5 ? 4 : 3; // per candidate: r, g, b [, a] (ref :986-990)
 	extern __shared__ __align__(16) uint8_t smem[];
 	const int wi = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int nblocks = v.blocks_w * v.blocks_h;
-	const int t = blockIdx.x * kSearchWarps + wi;
-	if (t >= nblocks)
+	const unsigned chunk = blockIdx.x * kSearchWarps + wi;
+	if (chunk >= nchunks)
 		return;
+	const int nblocks = v.blocks_w * v.blocks_h;
+	const int b0 = (int) chunk * kSearchChunkBlocks;
+	const int nb = min(kSearchChunkBlocks, nblocks - b0);
 
-	uint8_t *wbase = smem + (size_t) wi * warp_bytes;
-	uint32_t *px = reinterpret_cast<uint32_t *>(wbase);                                     // [16]
-	uint32_t *rows = reinterpret_cast<uint32_t *>(wbase + 64);                              // [(mcap+16)][kPitch]
-	uint4 *q8 = reinterpret_cast<uint4 *>(rows + (size_t) (mcap + 16) * kPitch);            // [(mcap+16)] quantised rows
-	uint32_t *cneg = reinterpret_cast<uint32_t *>(q8 + (mcap + 16));                        // [(mcap+16)]
-	uint32_t *col = cneg + (mcap + 16);                                                     // [mcap]
-	Feat *feat = reinterpret_cast<Feat *>(col + mcap);                                      // [mcap] features (32-bit metrics) or scaled colours
+	const WarpLayout L = warp_layout(mcap, kPack);
+	uint8_t *wbase = smem + (size_t) wi * L.total;
+	uint32_t *texels = reinterpret_cast<uint32_t *>(wbase + L.texels); // [16], texel y * 4 + x of the current block
+	uint32_t *rows = reinterpret_cast<uint32_t *>(wbase + L.rows);
+	uint4 *q8 = reinterpret_cast<uint4 *>(wbase + L.q8);
+	uint32_t *cneg = reinterpret_cast<uint32_t *>(wbase + L.cneg);
+	uint32_t *col = reinterpret_cast<uint32_t *>(wbase + L.col);
+	Feat *feat = reinterpret_cast<Feat *>(wbase + L.feat);
+	uint32_t *list = reinterpret_cast<uint32_t *>(wbase + L.feat);
+	uint32_t *ring = reinterpret_cast<uint32_t *>(wbase + L.rows);
+	uint32_t *cnt = reinterpret_cast<uint32_t *>(wbase + L.misc);
 
-	const int by = t / v.blocks_w, bx = t - by * v.blocks_w;
-	const int x0 = bx * 4, y0 = by * 4;
-	const int w = min(4, v.width - x0), h = min(4, v.rows - y0);
-
-	// 1. texels -> shared
-	if (lane < 4) {
-		uint32_t r[4];
-		load_block_row(v, x0, y0 + lane, w, r);
-#pragma unroll
-		for (int x = 0; x < 4; ++x)
-			px[lane * 4 + x] = r[x];
-	}
-	__syncwarp();
-
-	// 2. gather in the reference's column-major order (ref :940-959); bit o = x*4+y
-	// lane o < 16 looks at texel (x, y) = (o >> 2, o & 3); one ballot gives the mask of gathered texels
-	const uint32_t valid = valid_mask(w, h);
-	const int ti = (lane & 3) * 4 + ((lane >> 2) & 3); // texel index y * 4 + x of lane o
-	const uint32_t mine = px[ti];
-	bool use = lane < 16 && ((valid >> ti) & 1u);
-	if (DXT == kDxt1)
-		use = use && (mine >> 24) != 0;
-	const uint32_t usemask = __ballot_sync(0xFFFFFFFFu, use);
-	int n = __popc(usemask);
-	if (use)
-		col[__popc(usemask & ((1u << lane) - 1u))] = mine;
-	if (n == 0) {
-		if (lane == 0)
-			col[0] = 0;
-		n = 1;
-	}
-	{ // ref :962-993, candidates pre-generated by random_candidates_kernel
-		const size_t cb = (size_t) t * nrandom;
-		for (int k = lane; k < nrandom; k += 32) {
-			uint32_t c = from565(cand_c[cb + k]);
-			if (DXT == kDxt5)
-				c |= (uint32_t) cand_a[cb + k] << 24;
-			col[n + k] = c;
-		}
-	}
-	const int m = n + nrandom;
-	const int mpad = (m + 15) & ~15; // rows of the last tile beyond m are zero-filled
-	__syncwarp();
-
-	// 3. distance matrix, columns zero-padded to 16 (ref :375-392; argument order matters for SRGB)
-	if constexpr (kPack) {
-		// AVG / WAVG / W0AVG: the metric's feature is the colour with pre-scaled channel bytes and a distance is one
-		// per-byte subtraction + IDP.4A (colordist.cuh)
-		uint32_t *cvec = reinterpret_cast<uint32_t *>(feat); // [mcap]
-		for (int i = lane; i < m; i += 32)
-			cvec[i] = M::feat(col[i]).v;
-		__syncwarp();
-		// lane -> one packed word per row (texel columns 2kq, 2kq+1), 4 rows per step; everything the lane needs from its
-		// columns is loop-invariant.  Reads of cvec beyond m return leftovers that the masks discard.
-		const int kq = lane & 7;
-		const uint32_t ck0 = cvec[2 * kq], ck1 = cvec[2 * kq + 1];
-		const uint32_t kmask = (2 * kq < n ? 0x0000FFFFu : 0u) | (2 * kq + 1 < n ? 0xFFFF0000u : 0u);
-#pragma unroll 2
-		for (int i = lane >> 3; i < mpad; i += 4) {
-			const uint32_t ci = cvec[i];
-			const uint32_t d0 = (uint32_t) M::dist(FeatBytes{ci}, FeatBytes{ck0}), d1 = (uint32_t) M::dist(FeatBytes{ci}, FeatBytes{ck1});
-			rows[i * kPitch + kq] = i < m ? ((d0 | (d1 << 16)) & kmask) : 0u;
-		}
-	} else {
-		for (int i = lane; i < m; i += 32)
-			feat[i] = M::feat(col[i]);
-		__syncwarp();
-		// lane -> texel column k, 2 rows per step
-		const int k = lane & 15;
-		const Feat fk = feat[k];
-		const bool kok = k < n;
-		for (int i = lane >> 4; i < mpad; i += 2) {
-			int d = 0;
-			if (i < m && kok && k != i) {
-				const Feat fi = feat[i];
-				d = (i < n && k < i) ? M::dist(fk, fi) : M::dist(fi, fk);
-			}
-			rows[i * kPitch + k] = (uint32_t) d;
-		}
-	}
-	__syncwarp();
-
-	// 4. colour pair scan
-	uint32_t cij;
-	if constexpr (M::kMayBeNegative) // SRGB: sums can wrap negative, no lower bound to prune with
-		cij = scan_tiles<kPack, true, true>(rows, m, lane);
-	else
-		cij = scan_pruned<kPack>(rows, q8, cneg, m, n, lane, sadj);
-	const uint32_t c0 = col[cij >> 16], c1 = col[cij & 0xFFFFu];
-	uint32_t a01 = 0;
-
-	if (DXT == kDxt5) { // ref :416-478; alpha rows are always 16-bit, at the 16-bit pitch inside the same buffer
-		__syncwarp();
-		{ // the fixed points 0 and 255 folded into every row: min(d[i][k], fix[k]) is stored (masked columns: fix = 0)
-			const int kq = lane & 7;
-			const uint32_t ak0 = col[2 * kq] >> 24, ak1 = col[2 * kq + 1] >> 24;
-			const uint32_t f0 = min(ak0 * ak0, (255u - ak0) * (255u - ak0)), f1 = min(ak1 * ak1, (255u - ak1) * (255u - ak1));
-			const uint32_t fixw = (2 * kq < n ? f0 : 0u) | (2 * kq + 1 < n ? f1 << 16 : 0u);
-#pragma unroll 2
-			for (int i = lane >> 3; i < mpad; i += 4) {
-				const uint32_t ai = col[i] >> 24;
-				const uint32_t t0 = ai - ak0, t1 = (ai - ak1) << 8; // wrapping: the squares are exact mod 2^32
-				rows[i * kPitch16 + kq] = i < m ? __vminu2(t1 * t1 + t0 * t0, fixw) : 0u;
-			}
-		}
-		__syncwarp();
-		// alpha sums < 16 * 65025 < 2^20, up to 4095 pairs (m <= 90) for the keyed scan
-		const uint32_t aij = scan_pruned<true>(rows, q8, cneg, m, n, lane, sadj);
-		a01 = (col[aij >> 16] >> 24) | ((col[aij & 0xFFFFu] >> 24) << 8);
-	}
+	// texel rows are fetched one block ahead: lane y < 4 holds row y of the next block
+	const int by0 = b0 / v.blocks_w, bx0 = b0 - by0 * v.blocks_w;
+	uint32_t nextrow[4] = {0u, 0u, 0u, 0u};
+	if (lane < 4)
+		load_block_row(v, bx0 * 4, by0 * 4 + lane, min(4, v.width - bx0 * 4), nextrow);
 	if (lane == 0)
-		ends[t] = make_uint2(to565(c0) | (to565(c1) << 16), a01);
-}
+		*cnt = 0;
+	uint32_t win = lane < kLag ? __ldg(windows + (size_t) lane * nchunks + chunk) : 0u;
+	const RandLane rl(lane, one);
+	int gen = 0; // draws of this chunk generated so far
+	int pos = 0; // first draw of the current block
+	uint2 result = make_uint2(0u, 0u);
+	__syncwarp();
 
-static size_t search_smem(int cd, int nrandom)
-{
-	const bool pack = cd == kAVG || cd == kWAVG || cd == kW0AVG;
-	return search_warp_bytes(16 + nrandom, pack, true) * kSearchWarps;
+	int bx = bx0, by = by0;
+	for (int bi = 0; bi < nb; ++bi, pos += kDraws * nrandom) {
+		const int w = min(4, v.width - bx * 4), h = min(4, v.rows - by * 4);
+		if (++bx == v.blocks_w) {
+			bx = 0;
+			++by;
+		}
+		if (lane < 4) {
+			*reinterpret_cast<uint4 *>(texels + lane * 4) = make_uint4(nextrow[0], nextrow[1], nextrow[2], nextrow[3]);
+			if (bi + 1 < nb)
+				load_block_row(v, bx * 4, by * 4 + lane, min(4, v.width - bx * 4), nextrow);
+		}
+		__syncwarp();
+		// 1. gather in the reference's column-major order (ref :940-959): lane o < 16 looks at texel (x, y) = (o >> 2, o & 3)
+		const uint32_t valid = (w == 4 && h == 4) ? 0xFFFFu : valid_mask(w, h);
+		const int ti = (lane & 3) * 4 + ((lane >> 2) & 3);
+		const uint32_t mine = texels[ti];
+		bool use = lane < 16 && ((valid >> ti) & 1u);
+		if (DXT == kDxt1)
+			use = use && (mine >> 24) != 0;
+		const uint32_t usemask = __ballot_sync(0xFFFFFFFFu, use);
+		int n = __popc(usemask);
+		const uint32_t first = usemask ? __shfl_sync(0xFFFFFFFFu, mine, __ffs(usemask) - 1) : 0u; // n == 0: black, alpha 0 (ref :952-959)
+		const bool flat_c = !__any_sync(0xFFFFFFFFu, use && ((mine ^ first) & 0x00FFFFFFu));
+		const bool flat_a = DXT != kDxt5 || !__any_sync(0xFFFFFFFFu, use && ((mine ^ first) >> 24));
+		// All gathered colours equal: the box has one colour, every candidate equals it, the matrix is zero and the reference
+		// keeps pair (0, 1) -- both endpoints are that colour.  Likewise for alpha.  The block's draws are still consumed.
+		uint32_t c01 = to565(first) * 0x10001u, a01 = (first >> 24) * 0x101u;
+		if (!(flat_c && flat_a)) {
+			if (use)
+				col[__popc(usemask & ((1u << lane) - 1u))] = mine;
+			if (n == 0) {
+				if (lane == 0)
+					col[0] = 0;
+				n = 1;
+			}
+			const int m = n + nrandom;
+			{ // 2. candidates (ref :962-993): lo + rand() % len per channel over the box of the gathered colours
+				uint32_t lo[4], len[4], rcp[4];
+#pragma unroll
+				for (int ch = 0; ch < kDraws; ++ch) {
+					const uint32_t val = (mine >> (8 * ch)) & 0xFFu;
+					lo[ch] = usemask ? __reduce_min_sync(0xFFFFFFFFu, use ? val : 255u) : 0u;
+					const uint32_t hi = usemask ? __reduce_max_sync(0xFFFFFFFFu, use ? val : 0u) : 0u;
+					len[ch] = hi - lo[ch] + 1u;
+					rcp[ch] = kRcp.v[len[ch]];
+				}
+				// the ring shares its memory with the distance rows: the outputs of the latest step (the only ones that can
+				// reach into this block) are put back from the window itself
+				if (gen > pos && lane < kLag)
+					ring[(gen - kLag + lane) & (kRing - 1)] = win >> 1;
+				for (int k0 = 0; k0 < nrandom; k0 += 32) {
+					const int need = pos + min(nrandom, k0 + 32) * kDraws;
+					while (gen < need) {
+						win = rl.step31(win);
+						if (gen + kLag > pos && lane < kLag)
+							ring[(gen + lane) & (kRing - 1)] = win >> 1;
+						gen += kLag;
+					}
+					__syncwarp();
+					const int k = k0 + lane;
+					if (k < nrandom) {
+						const int d0 = pos + k * kDraws;
+						uint32_t c = 0;
+#pragma unroll
+						for (int ch = 0; ch < kDraws; ++ch)
+							c |= (lo[ch] + mod_small(ring[(d0 + ch) & (kRing - 1)], len[ch], rcp[ch])) << (8 * ch);
+						col[n + k] = c;
+					}
+					__syncwarp();
+				}
+			}
+
+			// 3. distance matrix (ref :375-392; argument order matters for SRGB), columns >= n zero
+			if (!flat_c) {
+				if constexpr (kPack) {
+					// AVG / WAVG / W0AVG: the feature is the colour with pre-scaled channel bytes f (all < 128);
+					// d(i, k) = |f_i|^2 + |f_k|^2 - 2 f_i . f_k = two IDP.4A with the negated bytes of f_k and one add
+					uint32_t *cvec = reinterpret_cast<uint32_t *>(feat), *nrm = cvec + mcap;
+					for (int i = lane; i < m; i += 32) {
+						const uint32_t f = M::feat(col[i]).v;
+						cvec[i] = f;
+						nrm[i] = (uint32_t) __dp4a((int) f, (int) f, 0);
+					}
+					__syncwarp();
+					// lane -> texel columns 4 kq .. 4 kq + 3 of one row, 8 rows per step
+					const int kq = lane & 3;
+					uint32_t nf[4], nk[4];
+#pragma unroll
+					for (int c = 0; c < 4; ++c) {
+						const int k = 4 * kq + c; // k < 16 <= capacity; columns >= n are masked below
+						nf[c] = (0x80808080u - cvec[k]) ^ 0x80808080u; // per-byte negation (no borrow: bytes < 128)
+						nk[c] = nrm[k];
+					}
+					const uint32_t m01 = (4 * kq < n ? 0x0000FFFFu : 0u) | (4 * kq + 1 < n ? 0xFFFF0000u : 0u);
+					const uint32_t m23 = (4 * kq + 2 < n ? 0x0000FFFFu : 0u) | (4 * kq + 3 < n ? 0xFFFF0000u : 0u);
+					for (int i = lane >> 2; i < m; i += 8) {
+						const int fi = (int) cvec[i];
+						const uint32_t ni = nrm[i];
+						uint32_t d[4];
+#pragma unroll
+						for (int c = 0; c < 4; ++c)
+							d[c] = (uint32_t) __dp4a(fi, (int) nf[c], __dp4a(fi, (int) nf[c], (int) (ni + nk[c])));
+						*reinterpret_cast<uint2 *>(rows + i * kPitch + 2 * kq) = make_uint2((d[0] | (d[1] << 16)) & m01, (d[2] | (d[3] << 16)) & m23);
+					}
+				} else {
+					for (int i = lane; i < m; i += 32)
+						feat[i] = M::feat(col[i]);
+					__syncwarp();
+					// lane -> texel column k, 2 rows per step
+					const int k = lane & 15;
+					const Feat fk = feat[k];
+					const bool kok = k < n;
+					for (int i = lane >> 4; i < m; i += 2) {
+						int d = 0;
+						if (kok && k != i) {
+							const Feat fi = feat[i];
+							d = (i < n && k < i) ? M::dist(fk, fi) : M::dist(fi, fk);
+						}
+						rows[i * kPitch + k] = (uint32_t) d;
+					}
+				}
+				__syncwarp();
+
+				// 4. colour pair scan
+				uint32_t cij;
+				if constexpr (M::kMayBeNegative) // SRGB: sums can wrap negative, no lower bound to prune with
+					cij = scan_tiles<kPack, true, true>(rows, m, lane);
+				else
+					cij = pruned_search<kPack>(rows, q8, cneg, list, cnt, m, lane, sadj);
+				c01 = to565(col[cij >> 16]) | (to565(col[cij & 0xFFFFu]) << 16);
+			}
+
+			if (DXT == kDxt5 && !flat_a) { // 5. ref :416-478; alpha rows are always 16-bit, at the 16-bit pitch inside the same buffer
+				__syncwarp();
+				{ // the fixed points 0 and 255 folded into every row: min(d[i][k], fix[k]) is stored (masked columns: fix = 0)
+					const int kq = lane & 7;
+					const uint32_t ak0 = col[2 * kq] >> 24, ak1 = col[2 * kq + 1] >> 24;
+					const uint32_t f0 = min(ak0 * ak0, (255u - ak0) * (255u - ak0)), f1 = min(ak1 * ak1, (255u - ak1) * (255u - ak1));
+					const uint32_t fixw = (2 * kq < n ? f0 : 0u) | (2 * kq + 1 < n ? f1 << 16 : 0u);
+#pragma unroll 2
+					for (int i = lane >> 3; i < m; i += 4) {
+						const uint32_t ai = col[i] >> 24;
+						const uint32_t t0 = ai - ak0, t1 = (ai - ak1) << 8; // wrapping: the squares are exact mod 2^32
+						rows[i * kPitch16 + kq] = __vminu2(t1 * t1 + t0 * t0, fixw);
+					}
+				}
+				__syncwarp();
+				const uint32_t aij = pruned_search<true>(rows, q8, cneg, list, cnt, m, lane, sadj);
+				a01 = (col[aij >> 16] >> 24) | ((col[aij & 0xFFFFu] >> 24) << 8);
+			}
+			__syncwarp();
+		}
+		if (lane == bi)
+			result = make_uint2(c01, a01);
+	}
+	if (lane < nb)
+		ends[b0 + lane] = result;
 }
 
 template <int DXT, int CD>
-static cudaError_t launch_search_cd(int nrandom, const ImageView &v, const uint16_t *cand_c, const uint8_t *cand_a,
-		uint2 *ends, cudaStream_t stream)
+static cudaError_t launch_search_cd(int nrandom, const ImageView &v, const uint32_t *windows, unsigned nchunks, uint2 *ends, cudaStream_t stream)
 {
-	const int nblocks = v.blocks_w * v.blocks_h;
-	if (nblocks == 0)
+	if (nchunks == 0)
 		return cudaSuccess;
 	const int mcap = 16 + nrandom;
-	const size_t wb = search_warp_bytes(mcap, Packs16<CD>::value, true);
-	const size_t smem = wb * kSearchWarps;
+	const size_t smem = (size_t) warp_layout(mcap, Packs16<CD>::value).total * kSearchWarps;
 	auto kern = pair_search_kernel<DXT, CD>;
 	if (smem > 48 * 1024) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 		if (e != cudaSuccess)
 			return e;
 	}
-	const dim3 block(kSearchThreads), grid((nblocks + kSearchWarps - 1) / kSearchWarps);
 	static const int sadj = [] { const char *e = getenv("S2TC_B200_SADJ"); return e ? atoi(e) : 0; }();
-	kern<<<grid, block, smem, stream>>>(v, nrandom, mcap, wb, sadj, cand_c, cand_a, ends);
+	const dim3 block(kSearchThreads), grid((nchunks + kSearchWarps - 1) / kSearchWarps);
+	kern<<<grid, block, smem, stream>>>(v, nrandom, mcap, sadj, 1u, windows, nchunks, ends);
 	return cudaGetLastError();
 }
 
@@ -591,7 +689,7 @@ int pair_search_max_nrandom()
 	int lo = 0, hi = 1 << 15;
 	while (lo < hi) {
 		const int mid = (lo + hi + 1) / 2;
-		if (search_smem(kRGB, mid) <= 227 * 1024)
+		if ((size_t) warp_layout(16 + mid, false).total * kSearchWarps <= 227 * 1024)
 			lo = mid;
 		else
 			hi = mid - 1;
@@ -600,31 +698,33 @@ int pair_search_max_nrandom()
 }
 
 template <int DXT>
-static cudaError_t launch_search_dxt(int cd, int nrandom, const ImageView &v, const uint16_t *cand_c,
-		const uint8_t *cand_a, uint2 *ends, cudaStream_t stream)
+static cudaError_t launch_search_dxt(int cd, int nrandom, const ImageView &v, const uint32_t *windows, unsigned nchunks, uint2 *ends,
+		cudaStream_t stream)
 {
 	if (nrandom <= 0 || nrandom > pair_search_max_nrandom())
 		return cudaErrorInvalidValue; // nrandom <= 0 is served by the fused 16-candidate encoder (search16.inl)
 	switch (cd) {
-	case kRGB: return launch_search_cd<DXT, kRGB>(nrandom, v, cand_c, cand_a, ends, stream);
-	case kYUV: return launch_search_cd<DXT, kYUV>(nrandom, v, cand_c, cand_a, ends, stream);
-	case kSRGB: return launch_search_cd<DXT, kSRGB>(nrandom, v, cand_c, cand_a, ends, stream);
-	case kSRGB_MIXED: return launch_search_cd<DXT, kSRGB_MIXED>(nrandom, v, cand_c, cand_a, ends, stream);
-	case kAVG: return launch_search_cd<DXT, kAVG>(nrandom, v, cand_c, cand_a, ends, stream);
-	case kWAVG: return launch_search_cd<DXT, kWAVG>(nrandom, v, cand_c, cand_a, ends, stream);
-	case kW0AVG: return launch_search_cd<DXT, kW0AVG>(nrandom, v, cand_c, cand_a, ends, stream);
-	case kNORMALMAP: return launch_search_cd<DXT, kNORMALMAP>(nrandom, v, cand_c, cand_a, ends, stream);
+	case kRGB: return launch_search_cd<DXT, kRGB>(nrandom, v, windows, nchunks, ends, stream);
+	case kYUV: return launch_search_cd<DXT, kYUV>(nrandom, v, windows, nchunks, ends, stream);
+	case kSRGB: return launch_search_cd<DXT, kSRGB>(nrandom, v, windows, nchunks, ends, stream);
+	case kSRGB_MIXED: return launch_search_cd<DXT, kSRGB_MIXED>(nrandom, v, windows, nchunks, ends, stream);
+	case kAVG: return launch_search_cd<DXT, kAVG>(nrandom, v, windows, nchunks, ends, stream);
+	case kWAVG: return launch_search_cd<DXT, kWAVG>(nrandom, v, windows, nchunks, ends, stream);
+	case kW0AVG: return launch_search_cd<DXT, kW0AVG>(nrandom, v, windows, nchunks, ends, stream);
+	case kNORMALMAP: return launch_search_cd<DXT, kNORMALMAP>(nrandom, v, windows, nchunks, ends, stream);
 	default: return cudaErrorInvalidValue;
 	}
 }
 
-cudaError_t launch_pair_search(int dxt, int cd, int nrandom, const ImageView &v, const uint16_t *d_cand_c,
-		const uint8_t *d_cand_a, uint2 *d_ends, cudaStream_t stream)
+cudaError_t launch_pair_search(int dxt, int cd, int nrandom, const ImageView &v, const uint32_t *d_windows, uint2 *d_ends,
+		cudaStream_t stream)
 {
+	const long long nblocks = (long long) v.blocks_w * v.blocks_h;
+	const unsigned nchunks = (unsigned) ((nblocks + kSearchChunkBlocks - 1) / kSearchChunkBlocks);
 	switch (dxt) {
-	case kDxt1: return launch_search_dxt<kDxt1>(cd, nrandom, v, d_cand_c, d_cand_a, d_ends, stream);
-	case kDxt3: return launch_search_dxt<kDxt3>(cd, nrandom, v, d_cand_c, d_cand_a, d_ends, stream);
-	default: return launch_search_dxt<kDxt5>(cd, nrandom, v, d_cand_c, d_cand_a, d_ends, stream);
+	case kDxt1: return launch_search_dxt<kDxt1>(cd, nrandom, v, d_windows, nchunks, d_ends, stream);
+	case kDxt3: return launch_search_dxt<kDxt3>(cd, nrandom, v, d_windows, nchunks, d_ends, stream);
+	default: return launch_search_dxt<kDxt5>(cd, nrandom, v, d_windows, nchunks, d_ends, stream);
 	}
 }
 
