@@ -1,18 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- S2TC encode throughput on B200 (metric of BASELINE.json: encode Mblocks/s + roofline fraction).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config2|config3|defaults|config5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload config3|config2|defaults|config5|config4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (N > 1)
     python bench.py --impl reference ...        the reference's own CPU encoder on the host cores
 
-One "step" = one pass of the hot path (565 pre-pass -> [random candidates] -> pair search -> refinement
-and packing, or the fused fast kernel) over one texture resident in HBM.  At N > 1 every rank owns a
-contiguous range of block rows of one tall texture (weak scaling: 8192-row shard per GPU); the only
-exchange is the DITHER_SIMPLE carry (a 128-byte transfer function per rank).
+Default workload = BASELINE.json's north-star configuration: ONE 16384x16384 RGBA texture, DXT1, WAVG,
+S2TC_RANDOM_COLORS=64, S2TC_REFINE_COLORS=LOOP (config 3).  One "step" = one pass of the hot path (565 pre-pass ->
+random candidates + pair search -> refinement and packing, or the fused fast kernel) over that texture, resident in
+HBM.  At N > 1 the texture is STRONG-scaled: rank r owns the contiguous block rows [R r / N, R (r+1) / N) (SURVEY.md
+8e); the only exchange is the DITHER_SIMPLE carry (128-byte transfer functions, one all-gather); every rank writes its
+own slice of the output.  config4 (a batch of mip-mapped textures) shards whole textures instead.
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` goes through the
-reference-facing host call with host<->device copies in the timed region, `roofline` is for the
-dominant kernel, `cpu_baseline` is the reference CPU encoder timed on this host.
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput of the whole job, `e2e` goes through the
+host-facing call with host<->device copies in the timed region, `roofline` is for the dominant kernel (integer pipes
+for the search modes, HBM for the quick modes), `cpu_baseline` is the reference CPU encoder timed on this host.
 """
 import argparse
 import json
@@ -31,24 +33,30 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 # name -> (dxt, cd, nrandom, refine, width, height, generator)
 WORKLOADS = {
-    "config2": ("DXT5", "SRGB_MIXED", 0, "LOOP", 8192, 8192, "synth_rgba"),
     "config3": ("DXT1", "WAVG", 64, "LOOP", 16384, 16384, "synth_rgba"),
+    "config2": ("DXT5", "SRGB_MIXED", 0, "LOOP", 8192, 8192, "synth_rgba"),
     "defaults": ("DXT1", "WAVG", -1, "ALWAYS", 8192, 8192, "synth_rgba"),
     "config5": ("DXT5", "NORMALMAP", -1, "NEVER", 4096, 4096, "synth_normal"),
+    "config4": ("DXT3", "ALL8", -1, "ALWAYS", 2048, 2048, "synth_rgba"),   # 256 textures x full mip chain x 8 metrics
 }
 DXT = {"DXT1": 0, "DXT3": 1, "DXT5": 2}
-CD = {n: i for i, n in enumerate(["RGB", "YUV", "SRGB", "SRGB_MIXED", "AVG", "WAVG", "W0AVG", "NORMALMAP"])}
+CD_NAMES = ["RGB", "YUV", "SRGB", "SRGB_MIXED", "AVG", "WAVG", "W0AVG", "NORMALMAP"]
+CD = {n: i for i, n in enumerate(CD_NAMES)}
 REFINE = {"NEVER": 0, "ALWAYS": 1, "LOOP": 2}
 DITHER = {"NONE": 0, "SIMPLE": 1, "FLOYDSTEINBERG": 2}
 GL = {0: 0x83F1, 1: 0x83F2, 2: 0x83F3}
+# integer operations of one distance evaluation
+C_CD = {"AVG": 8, "WAVG": 8, "W0AVG": 8, "RGB": 18, "YUV": 18, "SRGB": 35, "SRGB_MIXED": 14, "NORMALMAP": 12}
 
 
 def read_peaks():
+    """(HBM GB/s, SM clock MHz, source)"""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+            d = json.load(f)
+        return float(d["hbm_gbs"]), float(d.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -112,6 +120,8 @@ def run_reference_arm(args, wl):
     if rank != 0:
         return
     dxt_n, cd_n, nrandom, refine_n, width, height, gen = wl
+    if args.workload == "config4":
+        cd_n = "WAVG"   # the CPU sample runs one of the eight metrics; the mip levels are separate calls of the same path
     dxt, cd, refine, dither = DXT[dxt_n], CD[cd_n], REFINE[refine_n], DITHER[args.dither]
     threads = os.cpu_count() or 1
     bw = (width + 3) // 4
@@ -130,9 +140,10 @@ def run_reference_arm(args, wl):
     sample = f"first {rows} of {(height + 3) // 4} block rows ({blocks} blocks) of the {width}x{height} texture per step"
     line = {
         "impl": "reference", "metric": "encode_mblocks_per_s", "value": value, "unit": "Mblocks/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak" if args.workload == "config4" else "strong",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": workload_config(args, wl),
+        "config": workload_config(args, wl, 1),
         "cpu_baseline": {"value": value, "unit": "Mblocks/s", "cores": threads, "kind": kind, "sample": sample,
                          "note": "565 pre-pass single-threaded as upstream, block rows over all host threads"},
         "e2e": {"value": value, "unit": "Mblocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -141,15 +152,60 @@ def run_reference_arm(args, wl):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, wl):
+def workload_config(args, wl, world):
     dxt_n, cd_n, nrandom, refine_n, width, height, gen = wl
+    if args.workload == "config4":
+        return {"workload": f"config4: batch of {args.textures} x {width}x{height} {gen} textures per GPU with full mip chains, "
+                            f"{dxt_n}, all 8 S2TC_COLORDIST_MODEs, S2TC_RANDOM_COLORS={nrandom}, S2TC_REFINE_COLORS={refine_n}, "
+                            f"S2TC_DITHER_MODE={args.dither}",
+                "sharding": "whole textures per GPU (batch split), no exchange",
+                "l2": f"{args.textures} textures x {width * height * 4 >> 20} MiB per GPU exceed the 126 MiB L2; no flush needed"}
+    per_gpu = width * height * 4 // max(world, 1)
     return {"workload": f"{args.workload}: {dxt_n} {width}x{height} {gen}, S2TC_COLORDIST_MODE={cd_n}, "
                         f"S2TC_RANDOM_COLORS={nrandom}, S2TC_REFINE_COLORS={refine_n}, S2TC_DITHER_MODE={args.dither}",
-            "per_gpu_texture": f"{width}x{height} RGBA8", "sharding": "block rows of one tall texture, one shard per GPU",
-            "l2": (f"inputs {width * height * 4 >> 20} MiB per GPU exceed the 126 MiB L2; no flush needed"
-                   if width * height * 4 > (126 << 20) else
-                   f"inputs {width * height * 4 >> 20} MiB per GPU FIT the 126 MiB L2 (a --size/--workload choice for "
-                   f"debugging or profiling, not a bench configuration)")}
+            "texture": f"{width}x{height} RGBA8", "sharding": f"contiguous block rows of the one texture, {world} shard(s)",
+            "l2": (f"inputs {per_gpu >> 20} MiB per GPU exceed the 126 MiB L2; no flush needed"
+                   if per_gpu > (126 << 20) else
+                   f"inputs {per_gpu >> 20} MiB per GPU FIT the 126 MiB L2: a {max(per_gpu, 192 << 20) >> 20} MiB buffer is "
+                   f"rewritten between timed steps to flush it")}
+
+
+def gathered_counts(red, dxt):
+    """Histogram of n = colours the reference gathers per block (s2tc_algorithm.cpp:940-959) from the reduced texels."""
+    h, w = red.shape[:2]
+    bh, bw = (h + 3) // 4, (w + 3) // 4
+    valid = np.zeros((bh * 4, bw * 4), bool)
+    valid[:h, :w] = True if dxt != 0 else (red[..., 3] != 0)
+    n = valid.reshape(bh, 4, bw, 4).sum((1, 3)).ravel()
+    n = np.maximum(n, 1)   # empty block: one black candidate (:952-959)
+    return np.bincount(n, minlength=17)
+
+
+def search_ops(hist, nrandom, dxt, cd_n):
+    """Algorithmic integer operations per block of the pair search: one min + one add per (pair, texel)
+    for the colours and again for DXT5 alpha (the two fixed points folded into the rows), plus the distance evaluations
+    of the matrix fill.  Returned as (16-bit-packable ops, 32-bit ops), means over the blocks of `hist`."""
+    tot = hist.sum()
+    ops16 = ops32 = 0.0
+    for n in range(1, 17):
+        if not hist[n]:
+            continue
+        m = n + max(nrandom, 0)
+        if nrandom <= 0 and n == 1:
+            m = 2
+        p = m * (m - 1) // 2
+        pair = p * n * 2
+        dist = (n * (n - 1) // 2 + (m - n) * n) * C_CD[cd_n]
+        f = hist[n] / tot
+        if cd_n in ("AVG", "WAVG", "W0AVG"):
+            ops16 += f * pair
+        else:
+            ops32 += f * pair
+        ops32 += f * dist
+        if dxt == 2:
+            ops16 += f * pair
+            ops32 += f * (n * (n - 1) // 2 + (m - n) * n) * 3
+    return ops16, ops32
 
 
 def main():
@@ -158,9 +214,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="config2", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="config3", choices=list(WORKLOADS))
     ap.add_argument("--dither", default="SIMPLE", choices=list(DITHER))
     ap.add_argument("--size", type=int, default=0, help="override texture width=height (debug)")
+    ap.add_argument("--textures", type=int, default=32, help="config4: textures per GPU")
     ap.add_argument("--cpu-blocks", type=float, default=0, help="blocks per CPU sample step (0 = auto)")
     ap.add_argument("--cpu-rows", type=int, default=0)
     ap.add_argument("--no-check", action="store_true")
@@ -173,7 +230,7 @@ def main():
     wl = tuple(wl)
     if not args.cpu_blocks:
         # ~10-30 s of single-core work spread over the host threads (reference speeds from BASELINE.md)
-        per_core = {"config2": 0.16e6, "config3": 0.03e6, "defaults": 1.9e6, "config5": 0.2e6}[args.workload]
+        per_core = {"config2": 0.16e6, "config3": 0.03e6, "defaults": 1.9e6, "config5": 0.2e6, "config4": 1.9e6}[args.workload]
         args.cpu_blocks = per_core * 16
 
     if args.impl == "reference":
@@ -187,7 +244,6 @@ def main():
 
     import torch
     import s2tc_b200
-    from s2tc_b200 import Settings
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -197,98 +253,144 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the encoder has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    if args.workload == "config4":
+        import bench_batch
+        line = bench_batch.run(args, wl, world, rank, local, dist, ClockSampler, read_peaks, workload_config, cpu_reference_run)
+    else:
+        line = run_texture(args, wl, world, rank, local, dist)
+    if rank == 0:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's threads (and therefore the pages its pinned buffers are first touched on) to the CPUs of the NUMA
+    node its GPU hangs off, so that eight ranks do not all stage their uploads through one socket."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (w >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
+def run_texture(args, wl, world, rank, local, dist):
+    import torch
+    import s2tc_b200
+    from s2tc_b200 import Settings
+
     dxt_n, cd_n, nrandom, refine_n, width, height, gen = wl
     st = Settings(DXT[dxt_n], CD[cd_n], nrandom, REFINE[refine_n], DITHER[args.dither])
+    if st.dither == 2 and world > 1:
+        raise SystemExit("bench.py: DITHER_FLOYDSTEINBERG is a whole-image recurrence; it cannot be row-sharded (use --gpus 1)")
     bs = s2tc_b200.block_bytes(st.dxt)
     abits = {0: 1, 1: 4, 2: 8}[st.dxt]
     bw, bh = (width + 3) // 4, (height + 3) // 4
-    blocks = bw * bh
-    total_h = height * world
-    row0, row1 = rank * bh, (rank + 1) * bh
-    dpb = s2tc_b200.draws_per_block(st.dxt, nrandom)
+    total_blocks = bw * bh
+    row0, row1 = (bh * rank) // world, (bh * (rank + 1)) // world
+    my_rows = row1 - row0
+    my_blocks = my_rows * bw
+    y0, y1 = row0 * 4, min(row1 * 4, height)
 
     enc = s2tc_b200.Encoder(local)
-    img = make_image(gen, width, height, 1234 + rank)
-    h_src = torch.from_numpy(img).pin_memory()
-    h_dst = torch.empty(blocks * bs, dtype=torch.uint8).pin_memory()
+    img = make_image(gen, width, height, 1234)        # every rank regenerates the texture and keeps its rows
+    mine = np.ascontiguousarray(img[y0:y1])
+    h_src = torch.from_numpy(mine).pin_memory()
+    h_dst = torch.empty(max(my_blocks * bs, 1), dtype=torch.uint8).pin_memory()
     d_src = h_src.cuda(non_blocking=False)
-    d_dst = torch.empty(blocks * bs, dtype=torch.uint8, device="cuda")
+    d_dst = torch.empty(max(my_blocks * bs, 1), dtype=torch.uint8, device="cuda")
     # a non-default stream: its handle is what the C ABI launches on, and torch events recorded on it
     # bracket exactly those launches (the legacy default stream's handle is 0 = "use the context's own")
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    
-    def incoming_carry():
-        """DITHER_SIMPLE across shards: all-gather the 128-byte transfer functions, fold the lower ranks."""
-        if world == 1 or st.dither != 1:
-            return None
-        maps = enc.dither_summary_device(d_src, width, total_h, 4, abits, row0, row1, stream=stream.cuda_stream)
-        mine = torch.tensor([m - (1 << 64) if m >= (1 << 63) else m for m in maps], dtype=torch.int64, device="cuda")
-        gathered = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(gathered, mine)
-        carry = [0, 0, 0, 0]
-        for r in range(rank):
-            m = [int(x) & ((1 << 64) - 1) for x in gathered[r].tolist()]
-            carry = enc.carry_apply(m, 4, abits, carry)
-        return carry
-
-    maps_mine = torch.zeros(16, dtype=torch.int64, device="cuda")
-    maps_all = torch.zeros(16 * world, dtype=torch.int64, device="cuda")
+    NSLAB = 8
+    maps_mine = torch.zeros(16 * NSLAB, dtype=torch.int64, device="cuda")
+    maps_all = torch.zeros(16 * NSLAB * world, dtype=torch.int64, device="cuda")
+    maps1_all = torch.zeros(16 * world, dtype=torch.int64, device="cuda")
     carry_dev = torch.zeros(4, dtype=torch.int32, device="cuda")
+    per_gpu_bytes = (y1 - y0) * width * 4
+    flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda") if per_gpu_bytes <= (126 << 20) else None
 
     def step_device():
+        if flush is not None:
+            flush.add_(1)      # rewrite a buffer larger than the L2 between steps
         if world == 1:
-            enc.encode_rows_device(d_src, width, total_h, 4, row0, row1, d_dst, st, cursor0=0, carry=None,
-                                   stream=stream.cuda_stream)
+            enc.encode_rows_device(d_src, width, height, 4, 0, bh, d_dst, st, cursor0=0, carry=None, stream=stream.cuda_stream)
         else:   # summary -> all-gather (128 B per rank, NCCL) -> fold -> encode, all on the device, no host sync
-            enc.sharded_encode_async(d_src, width, total_h, 4, row0, row1, d_dst, st, maps_mine,
-                                     lambda: dist.all_gather_into_tensor(maps_all, maps_mine), maps_all, rank, carry_dev,
+            enc.sharded_encode_async(d_src, width, height, 4, row0, row1, d_dst, st, maps_mine[:16],
+                                     lambda: dist.all_gather_into_tensor(maps1_all, maps_mine[:16]), maps1_all, rank, carry_dev,
                                      cursor0=0, stream=stream.cuda_stream)
 
     def step_e2e():
         if world == 1:
             enc.compress(h_src, st, cursor=0, out=h_dst)   # the reference-facing host call, pinned buffers
-        else:
-            d_src.copy_(h_src, non_blocking=True)
-            step_device()
-            h_dst.copy_(d_dst, non_blocking=True)
-            torch.cuda.synchronize()
+        else:               # the same slab pipeline per shard; the carry exchange happens when every shard has been summarised
+            enc.compress_shard(h_src, width, height, row0, row1, h_dst, st, rank, NSLAB, maps_mine, maps_all,
+                               lambda: dist.all_gather_into_tensor(maps_all, maps_mine), cursor0=0, stream=stream.cuda_stream)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- correctness gate on rank 0: the first block rows against the oracle ----------------------
+    def all_ok(ok):
+        if dist is None:
+            return ok
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    # ---- correctness gate on EVERY rank: the first and last block rows of its shard against the oracle ---------------
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
     checked = None
-    if not args.no_check and rank == 0:
+    if not args.no_check:
         import _oracle as O
-        rows = max(1, min(bh, 32768 // bw))
+        ok = True
+        got_dev = d_dst[:my_blocks * bs].cpu().numpy()
         if st.dither == 2:
             # Floyd-Steinberg: the alpha pass of the reference is seeded from the LAST image row (DESIGN.md 5.2), so a
             # cropped image is not a prefix of the full one; check a smaller whole image through the same code path
             small = np.ascontiguousarray(img[:256, :256])
-            got_small = enc.compress(small, st)
-            if not np.array_equal(got_small, O.orc_compress(small, st.dxt, st.cd, st.nrandom, st.refine, st.dither)):
-                raise SystemExit("bench.py: GPU output differs from the oracle; refusing to report a number")
-            rows = 0
-        want = O.orc_compress(img[:rows * 4], st.dxt, st.cd, st.nrandom, st.refine, st.dither) if rows else np.zeros(0, np.uint8)
-        got = d_dst[:rows * bw * bs].cpu().numpy()
-        if not np.array_equal(got, want):
+            ok = np.array_equal(enc.compress(small, st), O.orc_compress(small, st.dxt, st.cd, st.nrandom, st.refine, st.dither))
+            checked = 64 * 64
+        else:
+            nrows = max(1, min(my_rows, (16384 if nrandom > 0 else 32768) // bw // 2))
+            spans = [(row0, row0 + nrows)] if my_rows <= 2 * nrows else [(row0, row0 + nrows), (row1 - nrows, row1)]
+            checked = 0
+            for a, b in spans:
+                want = O.orc_rows(img, st.dxt, st.cd, st.nrandom, st.refine, st.dither, (a, b), cursor=0)
+                ok = ok and np.array_equal(got_dev[(a - row0) * bw * bs:(b - row0) * bw * bs], want)
+                checked += (b - a) * bw
+        step_e2e()     # and the host path of this rank must give the same bytes as its device path
+        torch.cuda.synchronize()
+        ok = ok and np.array_equal(h_dst[:my_blocks * bs].numpy(), got_dev)
+        if not all_ok(ok):
             raise SystemExit("bench.py: GPU output differs from the oracle; refusing to report a number")
-        checked = rows * bw
+        if dist is not None:
+            t = torch.tensor([checked], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t)
+            checked = int(t.item())
+    del img
 
     # ---- timed region: device-resident -------------------------------------------------------------
-    enc.profile(True)
-    enc.profile_read(reset=True)
     launches0 = enc.launch_count()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -303,13 +405,28 @@ def main():
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     ms_total = ev0.elapsed_time(ev1)
     launches = enc.launch_count() - launches0
-    fam = enc.profile_read(reset=True)
-    enc.profile(False)
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
-    value = blocks * world / (ms_step * 1e-3) / 1e6
+    if flush is not None:      # the flush kernel is inside the events: time it alone and take it out
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(args.steps):
+            flush.add_(1)
+        f1.record(stream)
+        torch.cuda.synchronize()
+        ms_step -= f0.elapsed_time(f1) / args.steps
+    value = total_blocks / (ms_step * 1e-3) / 1e6
+
+    # ---- a second, untimed pass with per-family events: which kernel family dominates, and how long its launches take ----
+    enc.profile(True)
+    enc.profile_read(reset=True)
+    for _ in range(args.steps):
+        step_device()
+    fam = enc.profile_read(reset=True)
+    enc.profile(False)
 
     # ---- timed region: end to end through the host-facing call -------------------------------------
     e2e_steps = 0 if args.kernel_only else args.steps
@@ -324,50 +441,43 @@ def main():
     if dist is not None:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     ms_e2e = float(t_e2e.item()) / args.steps
-    e2e_value = blocks * world / (ms_e2e * 1e-3) / 1e6
+    e2e_value = total_blocks / (ms_e2e * 1e-3) / 1e6
+
+    # the entry point a drop-in user calls, with the memory they pass: tx_compress_dxtn on malloc'd (pageable) buffers
+    pageable = None
+    if world == 1 and e2e_steps:
+        os.environ.update({"S2TC_DITHER_MODE": args.dither, "S2TC_COLORDIST_MODE": cd_n, "S2TC_RANDOM_COLORS": str(nrandom),
+                           "S2TC_REFINE_COLORS": refine_n})
+        p_dst = np.zeros(my_blocks * bs, np.uint8)
+        reps = max(1, min(3, args.steps))
+        s2tc_b200.tx_compress_dxtn(4, width, height, mine, GL[st.dxt], p_dst, 0)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            s2tc_b200.lib().s2tc_b200_rand_cursor_set(0)
+            s2tc_b200.tx_compress_dxtn(4, width, height, mine, GL[st.dxt], p_dst, 0)
+        ms_p = (time.perf_counter() - t0) * 1e3 / reps
+        pageable = {"value": total_blocks / (ms_p * 1e-3) / 1e6, "ms_per_step": ms_p, "steps": reps,
+                    "path": "tx_compress_dxtn itself, S2TC_* from the environment, numpy (malloc'd, pageable) src and dest",
+                    "matches_pinned_path": bool(np.array_equal(p_dst, h_dst[:my_blocks * bs].numpy()))}
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+        return None
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------
-    peak_gbs, peak_src = read_peaks()
+    peak_gbs, sm_mhz, peak_src = read_peaks()
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
     dom = max(fam, key=lambda k: fam[k][0])
     dom_ms, dom_n = fam[dom]
-    if dom == "prepass":
-        dom_n //= 5   # maps, three scan launches and the replay are timed as one group
-    search_group = 2 if (nrandom <= 0 and st.dxt == 2) else 1   # search16 runs DXT5 as a colour launch + an alpha launch
-    if dom == "search":
-        dom_n //= search_group
-    dom_ms_launch = dom_ms / max(dom_n, 1)
-    per_launch_blocks = blocks * args.steps / max(dom_n, 1)
+    launch_group = {"prepass": 5 if world == 1 else 8, "candidates": 2}.get(dom, 1)   # launches timed as one group
+    if dom == "search" and nrandom <= 0 and st.dxt == 2:
+        launch_group = 2           # search16 runs DXT5 as a colour launch + an alpha launch
+    groups = max(dom_n // launch_group, 1)
+    dom_ms_launch = dom_ms / groups
+    per_launch_blocks = my_blocks * args.steps / groups
     # algorithmic bytes per block the kernel must move: 64 B of texels in, the kernel's result out
-    alg_bytes = {"fast": 64 + bs, "search": 64 + 8, "finish": 64 + 8 + bs, "prepass": 64 + 64, "candidates": 64 + nrandom * 2,
+    alg_bytes = {"fast": 64 + bs, "search": 64 + 8, "finish": 64 + 8 + bs, "prepass": 64 + 64, "candidates": 0.5,
                  "transcode": 2 * bs}[dom]
-    achieved = alg_bytes * per_launch_blocks / (dom_ms_launch * 1e-3) / 1e9 if dom_ms_launch > 0 else 0.0
-    # integer roofline of the pair search: one min + one add per (pair, texel), for colours and -- DXT5 --
-    # once more for alpha.  Rows whose distances fit 16 bits (alpha; the AVG-family metrics) are scanned two texels per
-    # instruction, so their share is rated against the packed peak: peak = ops / (ops32 / R_scalar + ops16 / R_packed).
-    peak_scalar, peak_packed = enc.int_peaks_gops()
-    n_pairs = (16 + max(nrandom, 0)) * (15 + max(nrandom, 0)) // 2
-    colour_ops = n_pairs * 16 * 2
-    colour16 = cd_n in ("AVG", "WAVG", "W0AVG")
-    ops32 = 0 if colour16 else colour_ops
-    ops16 = (colour_ops if colour16 else 0) + (colour_ops if st.dxt == 2 else 0)
-    int_ops_block = ops32 + ops16
-    search_n = fam["search"][1] // search_group
-    search_ms = fam["search"][0] / max(search_n, 1)
-    search_blocks = blocks * args.steps / max(search_n, 1)
-    int32 = None
-    if fam["search"][1] and peak_scalar and peak_packed:
-        a = int_ops_block * search_blocks / (search_ms * 1e-3) / 1e9
-        peak = int_ops_block / (ops32 / peak_scalar + ops16 / peak_packed)
-        int32 = {"kernel": "pair_search_kernel" if nrandom > 0 else "search16_kernel", "achieved": a, "peak": peak,
-                 "unit": "Gop/s (integer min+add)", "frac": a / peak,
-                 "ops_per_block": int_ops_block, "ops_per_block_32bit": ops32, "ops_per_block_16bit_packed": ops16,
-                 "peak_scalar": peak_scalar, "peak_packed16": peak_packed,
-                 "peak_source": "measured in this run (s2tc_b200_int_peaks: VIMNMX + IMAD on two pipes; VIMNMX.U16x2 + IDP.2A)"}
+    hbm_achieved = alg_bytes * per_launch_blocks / (dom_ms_launch * 1e-3) / 1e9 if dom_ms_launch > 0 else 0.0
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
@@ -378,41 +488,80 @@ def main():
                        "captured_blocks_per_launch": rec["blocks_per_launch"], "source": rec["source"]}
     except OSError:
         pass
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_block": alg_bytes, "ms_per_launch": dom_ms_launch,
-                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in fam.items() if v[1]},
-                "int32": int32}
+    hbm_view = {"achieved": hbm_achieved, "peak": peak_gbs, "unit": "GB/s", "frac": hbm_achieved / peak_gbs,
+                "algorithmic_bytes_per_block": alg_bytes, "peak_source": peak_src}
+    kernel_ms = {k: v[0] / args.steps for k, v in fam.items() if v[1]}
+    search_mode = nrandom >= 0 or cd_n == "NORMALMAP"
+    if search_mode and fam["search"][1]:
+        # Integer roofline.  Operations: what the reference's algorithm performs on THIS texture (the number of
+        # gathered colours per block comes from the reduced texels of rank 0's shard).  Peak: the issue ceiling of the SMs
+        # -- one warp instruction per scheduler and clock; a 32-bit min or add is one operation per lane, a packed 16-bit one
+        # is two -- at the SM clock of MEASURED_PEAKS.json; the rates the kernels' own instruction mixes sustain in a
+        # micro-benchmark of this run are reported beside it.
+        red = enc.rgb565_image(mine, abits, st.dither) if st.dxt == 0 else None
+        hist = gathered_counts(red if red is not None else mine, st.dxt)
+        ops16, ops32 = search_ops(hist, nrandom, st.dxt, cd_n)
+        nom16, nom32 = search_ops(np.bincount([16], minlength=17), nrandom, st.dxt, cd_n)
+        r32 = sms * 128 * sm_mhz * 1e6 / 1e9           # Gop/s, scalar
+        r16 = 2 * r32                                   # two 16-bit lanes per register
+        ops = ops16 + ops32
+        peak = ops / (ops32 / r32 + ops16 / r16)
+        s_launch_group = 2 if (nrandom <= 0 and st.dxt == 2) else 1
+        s_groups = max(fam["search"][1] // s_launch_group, 1)
+        s_ms = fam["search"][0] / s_groups
+        s_blocks = my_blocks * args.steps / s_groups
+        achieved = ops * s_blocks / (s_ms * 1e-3) / 1e9
+        peak_scalar, peak_packed = enc.int_peaks_gops()
+        roofline = {"bound": "int32", "kernel": "pair_search_kernel" if nrandom > 0 else "search16_kernel",
+                    "achieved": achieved, "peak": peak, "unit": "Gop/s", "frac": achieved / peak,
+                    "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                    "ms_per_launch": s_ms, "blocks_per_launch": s_blocks,
+                    "ops_per_block": ops, "ops_per_block_16bit_packed": ops16, "ops_per_block_32bit": ops32,
+                    "ops_per_block_if_every_block_had_16_colours": nom16 + nom32,
+                    "ops_definition": "reference algorithm on this texture: 2 per (pair, texel) for colours (+ the same for DXT5 "
+                                      "alpha) + distance evaluations of the matrix fill; n per block from the reduced texels",
+                    "note": "the pruned scan executes far fewer operations than the algorithm defines (pairs whose lower bound "
+                            "exceeds the best sum are never evaluated), so this is algorithmic work per second, not pipe occupancy"
+                            if nrandom > 0 else None,
+                    "peak_source": f"issue ceiling: {sms} SMs x 128 lanes x {sm_mhz:.0f} MHz (x2 for packed 16-bit operands)",
+                    "measured_mix_rates": {"scalar_gops": peak_scalar, "packed16_gops": peak_packed,
+                                           "how": "s2tc_b200_int_peaks in this run: VIMNMX + IMAD; VIMNMX.U16x2 + IDP.2A"},
+                    "kernel_ms_per_step": kernel_ms, "hbm": hbm_view}
+    else:
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": hbm_achieved, "peak": peak_gbs, "unit": "GB/s",
+                    "frac": hbm_achieved / peak_gbs, "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                    "traffic_detail": traffic, "peak_source": peak_src, "algorithmic_bytes_per_block": alg_bytes,
+                    "ms_per_launch": dom_ms_launch, "kernel_ms_per_step": kernel_ms,
+                    "whole_step": {"achieved": (64 + bs) * my_blocks / (ms_step * 1e-3) / 1e9,
+                                   "frac": (64 + bs) * my_blocks / (ms_step * 1e-3) / 1e9 / peak_gbs,
+                                   "note": "algorithmic bytes of the whole step (texels in, blocks out) over the step time"}}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----------------------------------------------------
     cpu = None
     if world == 1 and not args.kernel_only:
         threads = os.cpu_count() or 1
         rows = args.cpu_rows or max(4, min(bh, int(args.cpu_blocks // bw)))
-        kind, tp, tb, out = cpu_reference_run(img, st.dxt, st.cd, nrandom, st.refine, st.dither, rows, threads)
+        kind, tp, tb, out = cpu_reference_run(mine, st.dxt, st.cd, nrandom, st.refine, st.dither, rows, threads)
         same = bool(np.array_equal(out[:rows * bw * bs], d_dst[:rows * bw * bs].cpu().numpy()))
         cpu = {"value": rows * bw / (tp + tb) / 1e6, "unit": "Mblocks/s", "cores": threads, "kind": kind,
                "sample": f"first {rows} of {bh} block rows ({rows * bw} blocks): pre-pass {tp:.2f} s on 1 thread + "
                          f"blocks {tb:.2f} s on {threads} threads",
                "matches_gpu_output": same}
 
-    line = {
+    return {
         "metric": "encode_mblocks_per_s", "value": value, "unit": "Mblocks/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int32", "data": "synthetic", "config": workload_config(args, wl),
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic", "config": workload_config(args, wl, world),
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "Mblocks/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": width * height * 4,
-                "d2h_bytes_per_step": blocks * bs,
+                "d2h_bytes_per_step": total_blocks * bs,
                 "path": "s2tc_b200_compress_host (what tx_compress_dxtn calls), pinned host buffers" if world == 1
-                else "pinned H2D + s2tc_b200_encode_rows_device + D2H per rank"},
+                else "s2tc_b200_compress_host_shard per rank (slab-pipelined H2D / kernels / D2H, one all-gather of the "
+                     "DITHER_SIMPLE summaries), pinned host buffers",
+                "pageable": pageable},
         "gpu_launches": launches, "clocks": clocks,
         "checked_blocks_vs_oracle": checked,
     }
-    sys.stdout.flush()
-    os.dup2(saved_stdout, 1)
-    print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

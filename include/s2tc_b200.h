@@ -53,7 +53,10 @@ typedef struct s2tc_b200_settings {
 	int dither;  /* S2TC_DITHER_MODE                         (ref :161-173, default SIMPLE) */
 } s2tc_b200_settings;
 
-typedef struct s2tc_b200_ctx s2tc_b200_ctx; /* one per (thread, device); owns a stream and workspaces */
+/* One per (thread, device); owns a stream and the workspaces every call uses.  Calls on one context are serialised on the
+ * host by a mutex and ordered on the device: a call given a different stream than the previous call first waits (on the
+ * device) for that call's work, because the workspaces are shared.  Use one context per concurrent lane of work. */
+typedef struct s2tc_b200_ctx s2tc_b200_ctx;
 
 const char *s2tc_b200_last_error(void);
 int s2tc_b200_device_count(void);
@@ -103,6 +106,25 @@ int s2tc_b200_fold_carry_async(s2tc_b200_ctx *ctx, const void *d_all_maps, int r
 		void *stream);
 int s2tc_b200_encode_rows_async(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int srccomps, int width, int height,
 		const void *d_src_rows, int row0, int row1, void *d_dst, uint64_t rand_cursor0, int *d_carry, void *stream);
+/* _encode_rows_async for the caller that has just called _dither_summary_async for exactly these texels on this context
+ * and stream and has not modified them since: the maps the summary left in the workspace are reused (one of the three
+ * DITHER_SIMPLE phases is skipped).  Anything else than _fold_carry_async in between, or a different range or stream,
+ * and the maps are recomputed -- the result is the same either way as long as the texels are unchanged. */
+int s2tc_b200_encode_rows_after_summary_async(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int srccomps, int width, int height,
+		const void *d_src_rows, int row0, int row1, void *d_dst, uint64_t rand_cursor0, int *d_carry, void *stream);
+
+/* ---- one shard of an image from / to HOST memory (several GPUs or processes encode one texture together) ----------
+ * Block rows [row0, row1) of a width x height image; src_rows addresses texel row 4*row0, dest receives the shard's
+ * blocks (tight rows); rand_cursor0 is the cursor of the IMAGE's first block.  Uploads, kernels and downloads are
+ * pipelined in nslab pieces.  DITHER_SIMPLE: d_maps_mine (nslab*128 bytes, device) receives this shard's summaries;
+ * gather(user) is called once and must enqueue on `stream` an all-gather of every shard's d_maps_mine into d_maps_all
+ * (world*nslab*128 bytes, device, rank order) -- ncclAllGather, torch.distributed.all_gather_into_tensor ...; nslab
+ * (1..64) must be the same on every shard.  Other dither modes: gather is not called (FLOYDSTEINBERG cannot be sharded:
+ * S2TC_B200_EUNSUPPORTED).  Returns when the shard's blocks are in dest.  (the whole-image form is
+ * s2tc_b200_compress_host.) */
+int s2tc_b200_compress_host_shard(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int srccomps, int width, int height,
+		const uint8_t *src_rows, int row0, int row1, uint8_t *dest, uint64_t rand_cursor0, int rank, int nslab, void *d_maps_mine,
+		void *d_maps_all, void (*gather)(void *user), void *user, void *stream);
 
 /* ---- whole mip chain of an RGBA8 image on the device (SURVEY "next" N2) -----------------------------------
  * What the reference tool does per file after the DDS header (s2tc_compress.c:722-733): encode the level with

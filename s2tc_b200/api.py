@@ -27,6 +27,7 @@ _REFINE_NAMES = ["NEVER", "ALWAYS", "LOOP"]
 _DITHER_NAMES = ["NONE", "SIMPLE", "FLOYDSTEINBERG"]
 
 _u8p = C.POINTER(C.c_ubyte)
+GATHER_FN = C.CFUNCTYPE(None, C.c_void_p)   # the exchange callback of s2tc_b200_compress_host_shard
 
 
 class S2TCError(RuntimeError):
@@ -135,6 +136,8 @@ def lib():
     L.s2tc_b200_dither_summary_async.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, vp, vp]
     L.s2tc_b200_fold_carry_async.argtypes = [vp, vp, i32, i32, i32, vp, vp]
     L.s2tc_b200_encode_rows_async.argtypes = [vp, sp, i32, i32, i32, vp, i32, i32, vp, u64, vp, vp]
+    L.s2tc_b200_encode_rows_after_summary_async.argtypes = [vp, sp, i32, i32, i32, vp, i32, i32, vp, u64, vp, vp]
+    L.s2tc_b200_compress_host_shard.argtypes = [vp, sp, i32, i32, i32, vp, i32, i32, vp, u64, i32, i32, vp, vp, GATHER_FN, vp, vp]
     L.s2tc_b200_carry_apply.argtypes = [C.POINTER(u64), i32, i32, i32, i32]
     L.s2tc_b200_mipchain_bytes.argtypes = [i32, i32, i32]
     L.s2tc_b200_mipchain_bytes.restype = C.c_size_t
@@ -302,9 +305,21 @@ class Encoder:
                                                         _addr(maps_mine), stream))
             all_gather()
             _check(lib().s2tc_b200_fold_carry_async(self._ctx, _addr(maps_all), rank, comps, abits, _addr(carry_dev), stream))
-        _check(lib().s2tc_b200_encode_rows_async(self._ctx, C.byref(s), comps, width, height, _addr(src_rows), row0, row1,
-                                                 _addr(dst), cursor0, _addr(carry_dev) if settings.dither == DITHER_SIMPLE else None,
-                                                 stream))
+        _check(lib().s2tc_b200_encode_rows_after_summary_async(self._ctx, C.byref(s), comps, width, height, _addr(src_rows), row0,
+                                                               row1, _addr(dst), cursor0,
+                                                               _addr(carry_dev) if settings.dither == DITHER_SIMPLE else None, stream))
+
+    def compress_shard(self, src_rows, width, height, row0, row1, dst, settings, rank, nslab, maps_mine, maps_all, all_gather,
+                       cursor0=0, stream=None):
+        """Host to host: block rows [row0, row1) of a width x height image (src_rows: the shard's texel rows, a numpy
+        array or pinned torch tensor of shape (rows, width, comps)); pipelined in `nslab` pieces.  all_gather: a callable
+        that gathers `maps_mine` (nslab * 16 int64, device) of every rank into `maps_all` on `stream` (DITHER_SIMPLE)."""
+        s = settings.c()
+        comps = src_rows.shape[2]
+        cb = GATHER_FN(lambda _user: all_gather())
+        _check(lib().s2tc_b200_compress_host_shard(self._ctx, C.byref(s), comps, width, height, _addr(src_rows), row0, row1,
+                                                   _addr(dst), cursor0, rank, nslab, _addr(maps_mine), _addr(maps_all), cb, None,
+                                                   stream))
 
     def dither_summary_device(self, src_rows, width, height, comps, alphabits, row0, row1, stream=None):
         maps = (C.c_uint64 * 16)()

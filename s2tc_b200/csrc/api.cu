@@ -80,15 +80,22 @@ struct s2tc_b200_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
 	std::mutex mu;
-	DevBuf src, reduced, out, ends, dither_ws, plans, small, mip, rand_ws;
+	DevBuf src, reduced, out, ends, dither_ws, shard_ws, plans, small, mip, rand_ws;
 	RandPlan *h_plans = nullptr; // pinned ring
 	int plan_next = 0;
 	int *h_carry = nullptr; // pinned, 4 ints
 	uint64_t *h_summary = nullptr; // pinned, 16 words
 	uint8_t *h_block = nullptr;   // pinned, 64 + 16 bytes for the single-block path
-	const void *maps_src = nullptr; // dither workspace currently holds the maps of this texel range
+	// the dither workspace holds the chunk/tile maps of this texel range, left by a summary call on maps_stream; only
+	// s2tc_b200_encode_rows_after_summary_async may reuse them, and every other call forgets them
+	const void *maps_src = nullptr;
 	size_t maps_npix = 0;
 	int maps_comps = 0, maps_abits = 0;
+	cudaStream_t maps_stream = nullptr;
+	// workspaces are per context: a call on another stream than the previous one first waits for that call's work
+	cudaEvent_t last_done = nullptr;
+	cudaStream_t last_stream = nullptr;
+	bool last_valid = false;
 	uint64_t launches = 0;
 	bool profiling = false;
 	double fam_ms[kNumFam] = {0};
@@ -118,6 +125,28 @@ struct FamScope { // brackets a group of launches of one family with events when
 		if (a) {
 			cudaEventRecord(b, st);
 			c->pending.push_back({fam, a, b});
+		}
+	}
+};
+
+// Every entry point that enqueues work brackets it with this: the context's scratch buffers (reduced texels, endpoints,
+// dither maps, rand() windows, the small slots) are shared by all calls, so work enqueued on a different stream than the
+// previous call's is ordered behind it by an event.  Calls on one stream cost one event record.
+struct StreamOrder {
+	s2tc_b200_ctx *c;
+	cudaStream_t st;
+	StreamOrder(s2tc_b200_ctx *c_, cudaStream_t st_, bool keep_maps = false) : c(c_), st(st_)
+	{
+		if (c->last_valid && c->last_stream != st)
+			cudaStreamWaitEvent(st, c->last_done, 0);
+		if (!keep_maps)
+			c->maps_src = nullptr;
+	}
+	~StreamOrder()
+	{
+		if (cudaEventRecord(c->last_done, st) == cudaSuccess) {
+			c->last_stream = st;
+			c->last_valid = true;
 		}
 	}
 };
@@ -192,8 +221,10 @@ int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &
 }
 
 // d_src_rows: texel row 4*row0 of the image.  d_carry: device ints or NULL.
+// ready_ws: a dither workspace that already holds the chunk/tile maps of exactly these texels (phase 1 is skipped), or NULL.
 int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int width, int height,
-		const void *d_src_rows, int row0, int row1, void *d_dst, uint64_t cursor0, int *d_carry, cudaStream_t st)
+		const void *d_src_rows, int row0, int row1, void *d_dst, uint64_t cursor0, int *d_carry, cudaStream_t st,
+		void *ready_ws = nullptr)
 {
 	const int bh = (height + 3) / 4, bw = (width + 3) / 4;
 	if (width <= 0 || height <= 0 || row0 < 0 || row1 > bh || row0 > row1)
@@ -217,11 +248,9 @@ int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int
 			carry = (int *) c->small.p;
 			CU(cudaMemsetAsync(carry, 0, 4 * sizeof(int), st));
 		}
-		// a summary call on exactly these texels (sharded encodes do one to exchange carries) left their maps behind
-		const bool ready = c->maps_src == d_src_rows && c->maps_npix == npix && c->maps_comps == comps && c->maps_abits == abits;
-		c->maps_src = nullptr;
+		const bool ready = ready_ws != nullptr;
 		FamScope f(c, st, kFamPrepass, prepass_simple_launches(npix, ready));
-		CU(launch_prepass_simple(d_src_rows, comps, abits, npix, c->reduced.p, carry, c->dither_ws.p, ready, st));
+		CU(launch_prepass_simple(d_src_rows, comps, abits, npix, c->reduced.p, carry, ready ? ready_ws : c->dither_ws.p, ready, st));
 		texels = (const uint8_t *) c->reduced.p;
 		fmt = kSrcReduced;
 		texel_bytes = 4;
@@ -231,7 +260,6 @@ int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int
 					"(block rows [%d,%d) of %d requested)", row0, row1, bh);
 		CU(c->reduced.reserve(npix * 4));
 		CU(c->dither_ws.reserve(floyd_workspace_bytes(width, height)));
-		c->maps_src = nullptr;
 		FamScope f(c, st, kFamPrepass, comps == 4 && abits != 8 ? 2 : 1);
 		CU(launch_prepass_floyd(d_src_rows, comps, abits, width, height, c->reduced.p, c->dither_ws.p, st));
 		texels = (const uint8_t *) c->reduced.p;
@@ -253,16 +281,6 @@ int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int
 			return rc;
 	}
 	return 0;
-}
-
-bool is_pinned(const void *p)
-{
-	cudaPointerAttributes a;
-	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-		cudaGetLastError();
-		return false;
-	}
-	return a.type == cudaMemoryTypeHost;
 }
 
 } // namespace
@@ -298,17 +316,27 @@ int s2tc_b200_ctx_create(int device, s2tc_b200_ctx **out)
 	CU(cudaSetDevice(device));
 	s2tc_b200_ctx *c = new s2tc_b200_ctx();
 	c->device = device;
-	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-	CU(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
-	CU(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
-	CU(cudaHostAlloc((void **) &c->h_plans, sizeof(RandPlan) * kPlanRing, cudaHostAllocMapped));
-	CU(cudaHostAlloc((void **) &c->h_carry, 4 * sizeof(int), cudaHostAllocDefault));
-	CU(cudaHostAlloc((void **) &c->h_summary, 16 * sizeof(uint64_t), cudaHostAllocDefault));
-	CU(cudaHostAlloc((void **) &c->h_block, 128, cudaHostAllocDefault));
-	CU(c->plans.reserve(sizeof(RandPlan) * kPlanRing));
-	CU(c->small.reserve(1024));
-	CU(init_all_luts(c->stream)); // device-side tables of the metrics (one copy per translation unit), on this device
-	CU(cudaStreamSynchronize(c->stream));
+	const int rc = [&]() -> int {
+		CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+		CU(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+		CU(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+		CU(cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming));
+		CU(cudaHostAlloc((void **) &c->h_plans, sizeof(RandPlan) * kPlanRing, cudaHostAllocMapped));
+		CU(cudaHostAlloc((void **) &c->h_carry, 4 * sizeof(int), cudaHostAllocDefault));
+		CU(cudaHostAlloc((void **) &c->h_summary, 16 * sizeof(uint64_t), cudaHostAllocDefault));
+		CU(cudaHostAlloc((void **) &c->h_block, 128, cudaHostAllocDefault));
+		CU(c->plans.reserve(sizeof(RandPlan) * kPlanRing));
+		CU(c->small.reserve(1024));
+		CU(init_all_luts(c->stream)); // device-side tables of the metrics (one copy per translation unit), on this device
+		CU(cudaStreamSynchronize(c->stream));
+		return 0;
+	}();
+	if (rc) { // keep the message of the failing call; release whatever was created
+		const std::string msg = g_last_error;
+		s2tc_b200_ctx_destroy(c);
+		g_last_error = msg;
+		return rc;
+	}
 	*out = c;
 	return 0;
 }
@@ -318,21 +346,27 @@ void s2tc_b200_ctx_destroy(s2tc_b200_ctx *c)
 	if (!c)
 		return;
 	cudaSetDevice(c->device);
-	cudaStreamSynchronize(c->stream);
+	cudaDeviceSynchronize();
 	for (auto &p : c->pending) {
 		cudaEventDestroy(p.a);
 		cudaEventDestroy(p.b);
 	}
-	DevBuf *bufs[] = {&c->src, &c->reduced, &c->out, &c->ends, &c->dither_ws, &c->plans, &c->small, &c->mip, &c->rand_ws};
+	DevBuf *bufs[] = {&c->src, &c->reduced, &c->out, &c->ends, &c->dither_ws, &c->shard_ws, &c->plans, &c->small, &c->mip, &c->rand_ws};
 	for (DevBuf *b : bufs)
 		b->release();
 	cudaFreeHost(c->h_plans);
 	cudaFreeHost(c->h_carry);
 	cudaFreeHost(c->h_summary);
 	cudaFreeHost(c->h_block);
-	cudaStreamDestroy(c->stream);
-	cudaStreamDestroy(c->copy_in);
-	cudaStreamDestroy(c->copy_out);
+	if (c->last_done)
+		cudaEventDestroy(c->last_done);
+	if (c->stream)
+		cudaStreamDestroy(c->stream);
+	if (c->copy_in)
+		cudaStreamDestroy(c->copy_in);
+	if (c->copy_out)
+		cudaStreamDestroy(c->copy_out);
+	cudaGetLastError();
 	delete c;
 }
 
@@ -360,6 +394,7 @@ int s2tc_b200_encode_rows_device(s2tc_b200_ctx *c, const s2tc_b200_settings *sin
 	std::lock_guard<std::mutex> lock(c->mu);
 	CU(cudaSetDevice(c->device));
 	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	StreamOrder order(c, st);
 	int *d_carry = nullptr;
 	if (carry && s.dither == kDitherSimple) {
 		d_carry = (int *) c->small.p + 8;
@@ -392,13 +427,15 @@ int s2tc_b200_dither_summary_async(s2tc_b200_ctx *c, int srccomps, int alphabits
 	const int comps = srccomps == 3 ? 3 : 4;
 	const int y0 = row0 * 4, y1 = row1 * 4 < height ? row1 * 4 : height;
 	const size_t npix = (size_t) width * (y1 - y0);
+	StreamOrder order(c, st);
 	CU(c->dither_ws.reserve(dither_workspace_bytes(npix)));
 	FamScope f(c, st, kFamPrepass, kDitherSummaryLaunches);
 	CU(launch_dither_summary(d_src_rows, comps, alphabits, npix, (ByteMap *) d_maps, c->dither_ws.p, st));
-	c->maps_src = d_src_rows;
+	c->maps_src = d_src_rows; // for s2tc_b200_encode_rows_after_summary_async
 	c->maps_npix = npix;
 	c->maps_comps = comps;
 	c->maps_abits = alphabits;
+	c->maps_stream = st;
 	return 0;
 }
 
@@ -412,6 +449,7 @@ int s2tc_b200_fold_carry_async(s2tc_b200_ctx *c, const void *d_all_maps, int ran
 	std::lock_guard<std::mutex> lock(c->mu);
 	CU(cudaSetDevice(c->device));
 	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	StreamOrder order(c, st, /*keep_maps=*/true);
 	FamScope f(c, st, kFamPrepass, 1);
 	CU(launch_fold_carry((const ByteMap *) d_all_maps, rank, srccomps == 3 ? 3 : 4, alphabits, d_carry, st));
 	return 0;
@@ -429,7 +467,36 @@ int s2tc_b200_encode_rows_async(s2tc_b200_ctx *c, const s2tc_b200_settings *sin,
 	std::lock_guard<std::mutex> lock(c->mu);
 	CU(cudaSetDevice(c->device));
 	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	StreamOrder order(c, st);
 	return encode_rows(c, s, srccomps, width, height, d_src_rows, row0, row1, d_dst, rand_cursor0, d_carry, st);
+}
+
+// The same, for the caller that has just summarised exactly these texels with s2tc_b200_dither_summary_async on the same
+// context and stream and has NOT changed them since: the chunk/tile maps the summary left in the workspace are reused
+// (the first of the three DITHER_SIMPLE phases is skipped).  If the record of the last summary does not match this
+// range, or anything but s2tc_b200_fold_carry_async ran on the context in between, the maps are simply recomputed.
+int s2tc_b200_encode_rows_after_summary_async(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int srccomps, int width, int height,
+		const void *d_src_rows, int row0, int row1, void *d_dst, uint64_t rand_cursor0, int *d_carry, void *stream)
+{
+	if (!c || !d_src_rows || !d_dst)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	s2tc_b200_settings s;
+	if (int rc = settings_normalise(sin, s))
+		return rc;
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	const int comps = srccomps == 3 ? 3 : 4;
+	const int bh = (height + 3) / 4;
+	bool ready = false;
+	if (s.dither == kDitherSimple && width > 0 && height > 0 && row0 >= 0 && row1 <= bh && row0 < row1) {
+		const int y0 = row0 * 4, y1 = row1 * 4 < height ? row1 * 4 : height;
+		ready = c->maps_src == d_src_rows && c->maps_npix == (size_t) width * (y1 - y0) && c->maps_comps == comps &&
+				c->maps_abits == alpha_bits(s.dxt) && c->maps_stream == st;
+	}
+	StreamOrder order(c, st);
+	return encode_rows(c, s, srccomps, width, height, d_src_rows, row0, row1, d_dst, rand_cursor0, d_carry, st,
+			ready ? c->dither_ws.p : nullptr);
 }
 
 int s2tc_b200_dither_summary_device(s2tc_b200_ctx *c, int srccomps, int alphabits, int width, int height,
@@ -456,14 +523,11 @@ int s2tc_b200_dither_summary_device(s2tc_b200_ctx *c, int srccomps, int alphabit
 		}
 		return 0;
 	}
+	StreamOrder order(c, st);
 	CU(c->dither_ws.reserve(dither_workspace_bytes(npix)));
 	{
 		FamScope f(c, st, kFamPrepass, kDitherSummaryLaunches);
 		CU(launch_dither_summary(d_src_rows, comps, alphabits, npix, d_sum, c->dither_ws.p, st));
-		c->maps_src = d_src_rows; // encode_rows on the same texels may reuse the maps (same stream order assumed)
-		c->maps_npix = npix;
-		c->maps_comps = comps;
-		c->maps_abits = alphabits;
 	}
 	CU(cudaMemcpyAsync(c->h_summary, d_sum, 4 * sizeof(ByteMap), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
@@ -479,100 +543,155 @@ int s2tc_b200_carry_apply(const uint64_t map[4], int channel, int srccomps, int 
 	return bmap_apply(m, kind, carry_in);
 }
 
-int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int srccomps, int width, int height,
-		const uint8_t *src, uint8_t *dest, int dst_row_stride, uint64_t *rand_cursor)
+} // extern "C"
+
+namespace {
+
+// How a shard of a DITHER_SIMPLE image learns the carry entering it (s2tc_b200_compress_host_shard).
+struct CarryExchange {
+	int rank, nslab;          // this shard's position; summaries every shard contributes
+	ByteMap *d_mine, *d_all;  // nslab summaries of this shard; world * nslab summaries after `gather`
+	void (*gather)(void *);   // enqueues the all-gather of d_mine into d_all on the compute stream
+	void *user;
+};
+
+// Block rows [row0, row1) of a width x height image from host memory to host memory.  src_rows: texel row 4 * row0.
+// dest: first block of row0; row_bytes apart per block row.  st: the compute stream.
+//
+// Large ranges go through in slabs of block rows on three streams: while slab s is encoded, slab s+1 is on its way up
+// and slab s-1 on its way down (PCIe is full duplex), so the call costs about max(copy, kernels) instead of their sum.
+// The two pieces of cross-slab state stay on the device: the DITHER_SIMPLE carry (chained through d_carry on the
+// compute stream) and the rand cursor (closed form per block row).
+// With a CarryExchange (one shard of several, DITHER_SIMPLE) the work has two phases: every slab is summarised as it
+// lands (its chunk/tile maps stay in its own piece of workspace), the shards all-gather the summaries, each folds those
+// before it into its carry, and then the slabs are replayed from their maps, encoded and downloaded.
+int compress_rows_host(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int comps, int width, int height, const uint8_t *src_rows,
+		int row0, int row1, uint8_t *dest, size_t row_bytes, uint64_t cursor, const CarryExchange *ex, cudaStream_t st)
 {
-	if (!c || !src || !dest)
-		return fail(S2TC_B200_EINVAL, "NULL argument");
-	s2tc_b200_settings s;
-	if (int rc = settings_normalise(sin, s))
-		return rc;
-	if (width <= 0 || height <= 0)
-		return 0; // the reference's loops simply do not run
-	std::lock_guard<std::mutex> lock(c->mu);
-	CU(cudaSetDevice(c->device));
-	cudaStream_t st = c->stream;
-	const int comps = srccomps == 3 ? 3 : 4;
 	const int bw = (width + 3) / 4, bh = (height + 3) / 4, bs = block_bytes(s.dxt);
-	const size_t in_bytes = (size_t) width * height * comps;
-	const size_t tight = (size_t) bw * bs, out_bytes = tight * bh;
-	const uint64_t cursor = rand_cursor ? *rand_cursor : 0;
+	const int nrows = row1 - row0;
+	const int ty0 = row0 * 4, ty1 = row1 * 4 < height ? row1 * 4 : height;
+	const size_t in_bytes = (size_t) width * (ty1 - ty0) * comps;
+	const size_t tight = (size_t) bw * bs, out_bytes = tight * nrows;
+	const int abits = alpha_bits(s.dxt);
+	const bool exchange = ex && s.dither == kDitherSimple;
+	if (s.dither == kDitherFloyd && (row0 != 0 || row1 != bh))
+		return fail(S2TC_B200_EUNSUPPORTED, "DITHER_FLOYDSTEINBERG diffuses error between rows: encode the whole image in one call "
+				"(block rows [%d,%d) of %d requested)", row0, row1, bh);
 
 	CU(c->src.reserve(in_bytes));
 	CU(c->out.reserve(out_bytes));
-	// ref s2tc_libtxc_dxtn.cpp:243,261,279: a stride below width*2 (DXT1) / width*4 (DXT3/5) means tight rows
-	const size_t row_bytes = dst_row_stride >= width * (bs / 4) ? (size_t) dst_row_stride : tight;
-
-	// Large images go through in slabs of block rows on three streams: while slab s is encoded, slab s+1 is on
-	// its way up and slab s-1 on its way down (PCIe is full duplex), so the call costs about max(copy, kernels)
-	// instead of their sum.  The two pieces of cross-slab state stay on the device: the DITHER_SIMPLE carry
-	// (chained through d_carry on the compute stream) and the rand cursor (closed form per block row).
 	static const int slab_mb = [] { const char *e = getenv("S2TC_B200_SLAB_MB"); int n = e ? atoi(e) : 0; return n > 0 ? n : 16; }();
 	// ~16 MiB of texels per slab by default (measured on config 2: 32 / 16 / 8 MiB -> e2e 5.9 / 5.5 / 7.2 ms); with random
-	// candidates the kernels dominate the copies and every slab costs a jump-ahead plan on the host and a candidate
-	// launch that small slabs cannot fill: 4x larger slabs
+	// candidates the kernels dominate the copies and every slab costs a jump-ahead plan on the host: 4x larger slabs
 	int nslab = (int) (in_bytes / ((size_t) slab_mb << (s.nrandom > 0 ? 22 : 20)));
 	nslab = nslab < 1 ? 1 : (nslab > 64 ? 64 : nslab);
-	if (nslab > bh)
-		nslab = bh;
+	if (exchange)
+		nslab = ex->nslab; // every shard contributes the same number of summaries
+	if (nslab > nrows)
+		nslab = nrows;
 	if (row_bytes < tight || s.dither == kDitherFloyd)
 		nslab = 1; // overlapping destination rows: single ordered copy at the end; Floyd-Steinberg: one 2-D recurrence
 	int *d_carry = nullptr;
 	if (s.dither == kDitherSimple) {
 		d_carry = (int *) c->small.p + 8;
-		CU(cudaMemsetAsync(d_carry, 0, 4 * sizeof(int), st));
+		if (!exchange)
+			CU(cudaMemsetAsync(d_carry, 0, 4 * sizeof(int), st));
 	}
 	// S2TC_B200_TRACE=1: print when every slab's upload, kernels and download finished (ms since the call started)
 	static const bool trace = getenv("S2TC_B200_TRACE") && atoi(getenv("S2TC_B200_TRACE"));
 	const unsigned evflags = trace ? cudaEventDefault : cudaEventDisableTiming;
-	std::vector<cudaEvent_t> up(nslab), done(nslab), down(trace ? nslab : 0);
+	std::vector<cudaEvent_t> up(nslab, nullptr), done(nslab, nullptr), down(trace ? nslab : 0, nullptr);
+	std::vector<size_t> ws_off(nslab + 1, 0);
 	cudaEvent_t t0 = nullptr;
-	for (int i = 0; i < nslab; ++i) {
-		CU(cudaEventCreateWithFlags(&up[i], evflags));
-		CU(cudaEventCreateWithFlags(&done[i], evflags));
-		if (trace)
-			CU(cudaEventCreate(&down[i]));
-	}
-	if (trace) {
-		CU(cudaEventCreate(&t0));
-		CU(cudaEventRecord(t0, st));
-		if (nslab > 1) {
-			CU(cudaStreamWaitEvent(c->copy_in, t0, 0));
-			CU(cudaStreamWaitEvent(c->copy_out, t0, 0));
-		}
-	}
-	int rc = 0;
-	for (int i = 0; i < nslab && !rc; ++i) {
-		const int r0 = (int) ((long long) bh * i / nslab), r1 = (int) ((long long) bh * (i + 1) / nslab);
+	const bool pipelined = nslab > 1 || exchange;
+	auto slab_rows = [&](int i, int &r0, int &r1) {
+		r0 = row0 + (int) ((long long) nrows * i / nslab);
+		r1 = row0 + (int) ((long long) nrows * (i + 1) / nslab);
+	};
+	auto slab_texels = [&](int r0, int r1, size_t &off, size_t &len) {
 		const int y0 = r0 * 4, y1 = r1 * 4 < height ? r1 * 4 : height;
-		const size_t off = (size_t) y0 * width * comps, len = (size_t) (y1 - y0) * width * comps;
-		cudaStream_t sin_ = nslab > 1 ? c->copy_in : st, sout = nslab > 1 ? c->copy_out : st;
-		CU(cudaMemcpyAsync((uint8_t *) c->src.p + off, src + off, len, cudaMemcpyHostToDevice, sin_));
-		if (nslab > 1 || trace) {
-			CU(cudaEventRecord(up[i], sin_));
-			CU(cudaStreamWaitEvent(st, up[i], 0));
+		off = (size_t) (y0 - ty0) * width * comps;
+		len = (size_t) (y1 - y0) * width * comps;
+	};
+	// everything that can fail after the first enqueue runs inside this lambda; the streams are always drained and the
+	// events destroyed afterwards, so that no copy touches the caller's buffers once the call has returned
+	const int rc = [&]() -> int {
+		for (int i = 0; i < nslab; ++i) {
+			CU(cudaEventCreateWithFlags(&up[i], evflags));
+			CU(cudaEventCreateWithFlags(&done[i], evflags));
+			if (trace)
+				CU(cudaEventCreate(&down[i]));
 		}
-		uint8_t *d_out = (uint8_t *) c->out.p + (size_t) r0 * tight;
-		rc = encode_rows(c, s, comps, width, height, (const uint8_t *) c->src.p + off, r0, r1, d_out, cursor, d_carry, st);
-		if (rc)
-			break;
-		if (nslab > 1 || trace) {
-			CU(cudaEventRecord(done[i], st));
-			CU(cudaStreamWaitEvent(sout, done[i], 0));
+		if (pipelined || trace) {
+			CU(cudaEventCreateWithFlags(&t0, evflags));
+			CU(cudaEventRecord(t0, st));
+			if (pipelined) { // the copy streams start behind whatever the compute stream was given before this call
+				CU(cudaStreamWaitEvent(c->copy_in, t0, 0));
+				CU(cudaStreamWaitEvent(c->copy_out, t0, 0));
+			}
 		}
-		if (row_bytes == tight)
-			CU(cudaMemcpyAsync(dest + (size_t) r0 * tight, d_out, (size_t) (r1 - r0) * tight, cudaMemcpyDeviceToHost, sout));
-		else if (row_bytes > tight)
-			CU(cudaMemcpy2DAsync(dest + (size_t) r0 * row_bytes, row_bytes, d_out, tight, tight, r1 - r0, cudaMemcpyDeviceToHost, sout));
-		if (trace)
-			CU(cudaEventRecord(down[i], sout));
-	}
-	cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaSuccess, e3 = cudaSuccess;
-	if (nslab > 1) {
-		e2 = cudaStreamSynchronize(c->copy_in);
-		e3 = cudaStreamSynchronize(c->copy_out);
-	}
-	if (trace && !rc) {
+		cudaStream_t sin_ = pipelined ? c->copy_in : st, sout = pipelined ? c->copy_out : st;
+		if (exchange) { // phase A: upload + summarise slab by slab
+			for (int i = 0; i < nslab; ++i) {
+				int r0, r1;
+				size_t off, len;
+				slab_rows(i, r0, r1);
+				slab_texels(r0, r1, off, len);
+				ws_off[i + 1] = ws_off[i] + ((dither_workspace_bytes(len / comps) + 255) & ~(size_t) 255);
+			}
+			CU(c->shard_ws.reserve(ws_off[nslab]));
+			for (int i = 0; i < nslab; ++i) {
+				int r0, r1;
+				size_t off, len;
+				slab_rows(i, r0, r1);
+				slab_texels(r0, r1, off, len);
+				CU(cudaMemcpyAsync((uint8_t *) c->src.p + off, src_rows + off, len, cudaMemcpyHostToDevice, sin_));
+				CU(cudaEventRecord(up[i], sin_));
+				CU(cudaStreamWaitEvent(st, up[i], 0));
+				FamScope f(c, st, kFamPrepass, kDitherSummaryLaunches);
+				CU(launch_dither_summary((const uint8_t *) c->src.p + off, comps, abits, len / comps, ex->d_mine + 4 * i,
+						(uint8_t *) c->shard_ws.p + ws_off[i], st));
+			}
+			if (nslab < ex->nslab) { // a shard with fewer block rows than slabs: the missing ranges are empty
+				FamScope f(c, st, kFamPrepass, 1);
+				CU(launch_identity_maps(ex->d_mine + 4 * nslab, ex->nslab - nslab, comps, abits, st));
+			}
+			ex->gather(ex->user);
+			FamScope f(c, st, kFamPrepass, 1);
+			CU(launch_fold_carry(ex->d_all, ex->rank * ex->nslab, comps, abits, d_carry, st));
+		}
+		for (int i = 0; i < nslab; ++i) {
+			int r0, r1;
+			size_t off, len;
+			slab_rows(i, r0, r1);
+			slab_texels(r0, r1, off, len);
+			if (!exchange) {
+				CU(cudaMemcpyAsync((uint8_t *) c->src.p + off, src_rows + off, len, cudaMemcpyHostToDevice, sin_));
+				if (pipelined || trace) {
+					CU(cudaEventRecord(up[i], sin_));
+					CU(cudaStreamWaitEvent(st, up[i], 0));
+				}
+			}
+			uint8_t *d_out = (uint8_t *) c->out.p + (size_t) (r0 - row0) * tight;
+			if (int e = encode_rows(c, s, comps, width, height, (const uint8_t *) c->src.p + off, r0, r1, d_out, cursor, d_carry, st,
+						exchange ? (uint8_t *) c->shard_ws.p + ws_off[i] : nullptr))
+				return e;
+			if (pipelined || trace) {
+				CU(cudaEventRecord(done[i], st));
+				CU(cudaStreamWaitEvent(sout, done[i], 0));
+			}
+			if (row_bytes == tight)
+				CU(cudaMemcpyAsync(dest + (size_t) (r0 - row0) * tight, d_out, (size_t) (r1 - r0) * tight, cudaMemcpyDeviceToHost, sout));
+			else if (row_bytes > tight)
+				CU(cudaMemcpy2DAsync(dest + (size_t) (r0 - row0) * row_bytes, row_bytes, d_out, tight, tight, r1 - r0, cudaMemcpyDeviceToHost, sout));
+			if (trace)
+				CU(cudaEventRecord(down[i], sout));
+		}
+		return 0;
+	}();
+	const cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(c->copy_in), e3 = cudaStreamSynchronize(c->copy_out);
+	if (trace && !rc && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) {
 		for (int i = 0; i < nslab; ++i) {
 			float a = 0, b = 0, d = 0;
 			cudaEventElapsedTime(&a, t0, up[i]);
@@ -582,9 +701,11 @@ int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int
 		}
 	}
 	for (int i = 0; i < nslab; ++i) {
-		cudaEventDestroy(up[i]);
-		cudaEventDestroy(done[i]);
-		if (trace)
+		if (up[i])
+			cudaEventDestroy(up[i]);
+		if (done[i])
+			cudaEventDestroy(done[i]);
+		if (trace && down[i])
 			cudaEventDestroy(down[i]);
 	}
 	if (t0)
@@ -597,13 +718,83 @@ int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int
 	if (row_bytes < tight) { // rows overlap in dest (stride between width*bs/4 and the padded width): later rows win, as in the reference
 		std::vector<uint8_t> tmp(out_bytes);
 		CU(cudaMemcpy(tmp.data(), c->out.p, out_bytes, cudaMemcpyDeviceToHost));
-		for (int r = 0; r < bh; ++r)
+		for (int r = 0; r < nrows; ++r)
 			memcpy(dest + (size_t) r * row_bytes, tmp.data() + (size_t) r * tight, tight);
+	}
+	return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int s2tc_b200_compress_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int srccomps, int width, int height,
+		const uint8_t *src, uint8_t *dest, int dst_row_stride, uint64_t *rand_cursor)
+{
+	if (!c || !src || !dest)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	s2tc_b200_settings s;
+	if (int rc = settings_normalise(sin, s))
+		return rc;
+	if (width <= 0 || height <= 0)
+		return 0; // the reference's loops simply do not run
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	const int comps = srccomps == 3 ? 3 : 4;
+	const int bw = (width + 3) / 4, bh = (height + 3) / 4, bs = block_bytes(s.dxt);
+	const size_t tight = (size_t) bw * bs;
+	const uint64_t cursor = rand_cursor ? *rand_cursor : 0;
+	// ref s2tc_libtxc_dxtn.cpp:243,261,279: a stride below width*2 (DXT1) / width*4 (DXT3/5) means tight rows
+	const size_t row_bytes = dst_row_stride >= width * (bs / 4) ? (size_t) dst_row_stride : tight;
+	{
+		StreamOrder order(c, c->stream);
+		if (int rc = compress_rows_host(c, s, comps, width, height, src, 0, bh, dest, row_bytes, cursor, nullptr, c->stream))
+			return rc;
 	}
 	if (rand_cursor && s.nrandom > 0)
 		*rand_cursor = cursor + (uint64_t) bw * bh * draws_per_block(s.dxt, s.nrandom);
-	(void) is_pinned;
 	return 0;
+}
+
+// One shard of an image that several contexts (GPUs, processes) encode together, host memory to host memory: block rows
+// [row0, row1) of a width x height image; src_rows addresses texel row 4 * row0, dest the shard's first block (tight rows).
+// rand_cursor0 is the cursor of the IMAGE's first block.  For DITHER_SIMPLE the shards must learn the carry entering
+// them: d_maps_mine (nslab * 128 bytes, device) receives this shard's summaries, `gather(user)` is called once and must
+// enqueue, on `stream`, an all-gather of every shard's d_maps_mine into d_maps_all (world * nslab * 128 bytes, device, in
+// rank order) -- e.g. ncclAllGather / torch.distributed.all_gather_into_tensor.  nslab (1..64, the same on every shard) is
+// also the number of pieces the shard is pipelined in.  With another dither mode gather is never called.
+int s2tc_b200_compress_host_shard(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int srccomps, int width, int height,
+		const uint8_t *src_rows, int row0, int row1, uint8_t *dest, uint64_t rand_cursor0, int rank, int nslab, void *d_maps_mine,
+		void *d_maps_all, void (*gather)(void *), void *user, void *stream)
+{
+	if (!c || !src_rows || !dest)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	s2tc_b200_settings s;
+	if (int rc = settings_normalise(sin, s))
+		return rc;
+	const int bh = (height + 3) / 4;
+	if (width <= 0 || height <= 0 || row0 < 0 || row1 > bh || row0 > row1 || rank < 0)
+		return fail(S2TC_B200_EINVAL, "bad geometry %dx%d rows [%d,%d) rank %d", width, height, row0, row1, rank);
+	const bool exchange = s.dither == kDitherSimple && gather;
+	if (exchange && (!d_maps_mine || !d_maps_all || nslab < 1 || nslab > 64))
+		return fail(S2TC_B200_EINVAL, "DITHER_SIMPLE shards need d_maps_mine, d_maps_all and 1 <= nslab <= 64");
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	StreamOrder order(c, st);
+	const int comps = srccomps == 3 ? 3 : 4;
+	if (row0 == row1) { // an empty shard still takes part in the exchange
+		if (exchange) {
+			FamScope f(c, st, kFamPrepass, 1);
+			CU(launch_identity_maps((ByteMap *) d_maps_mine, nslab, comps, alpha_bits(s.dxt), st));
+			gather(user);
+			CU(cudaStreamSynchronize(st));
+		}
+		return 0;
+	}
+	CarryExchange ex{rank, nslab, (ByteMap *) d_maps_mine, (ByteMap *) d_maps_all, gather, user};
+	const size_t tight = (size_t) ((width + 3) / 4) * block_bytes(s.dxt);
+	return compress_rows_host(c, s, comps, width, height, src_rows, row0, row1, dest, tight, rand_cursor0, exchange ? &ex : nullptr, st);
 }
 
 size_t s2tc_b200_mipchain_bytes(int dxt, int width, int height)
@@ -627,6 +818,7 @@ int s2tc_b200_mip_reduce_device(s2tc_b200_ctx *c, const void *d_in, int width, i
 	std::lock_guard<std::mutex> lock(c->mu);
 	CU(cudaSetDevice(c->device));
 	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	StreamOrder order(c, st);
 	FamScope f(c, st, kFamPrepass, 1);
 	CU(launch_mip_reduce(d_in, width, height, d_out, st));
 	return 0;
@@ -645,6 +837,7 @@ int s2tc_b200_compress_mipchain_device(s2tc_b200_ctx *c, const s2tc_b200_setting
 	std::lock_guard<std::mutex> lock(c->mu);
 	CU(cudaSetDevice(c->device));
 	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	StreamOrder order(c, st);
 	uint64_t cursor = rand_cursor ? *rand_cursor : 0;
 	const int bs = block_bytes(s.dxt);
 	uint8_t *cur = (uint8_t *) d_rgba, *other = (uint8_t *) d_scratch, *dst = (uint8_t *) d_dst;
@@ -706,6 +899,7 @@ int s2tc_b200_rgb565_host(s2tc_b200_ctx *c, uint8_t *out, const uint8_t *src, in
 	std::lock_guard<std::mutex> lock(c->mu);
 	CU(cudaSetDevice(c->device));
 	cudaStream_t st = c->stream;
+	StreamOrder order(c, st);
 	const int comps = srccomps == 3 ? 3 : 4;
 	const int abits = (alphabits == 1 || alphabits == 4) ? alphabits : 8; // ref s2tc_algorithm.cpp:1437-1449
 	const size_t npix = (size_t) width * height;
@@ -717,14 +911,12 @@ int s2tc_b200_rgb565_host(s2tc_b200_ctx *c, uint8_t *out, const uint8_t *src, in
 		CU(launch_prepass_none(c->src.p, comps, abits, npix, c->reduced.p, st));
 	} else if (dither == kDitherFloyd) {
 		CU(c->dither_ws.reserve(floyd_workspace_bytes(width, height)));
-		c->maps_src = nullptr;
 		FamScope f(c, st, kFamPrepass, 2);
 		CU(launch_prepass_floyd(c->src.p, comps, abits, width, height, c->reduced.p, c->dither_ws.p, st));
 	} else {
 		CU(c->dither_ws.reserve(dither_workspace_bytes(npix)));
 		int *carry = (int *) c->small.p;
 		CU(cudaMemsetAsync(carry, 0, 4 * sizeof(int), st));
-		c->maps_src = nullptr;
 		FamScope f(c, st, kFamPrepass, prepass_simple_launches(npix, false));
 		CU(launch_prepass_simple(c->src.p, comps, abits, npix, c->reduced.p, carry, c->dither_ws.p, false, st));
 	}
@@ -747,6 +939,7 @@ int s2tc_b200_encode_block_host(s2tc_b200_ctx *c, const s2tc_b200_settings *sin,
 	std::lock_guard<std::mutex> lock(c->mu);
 	CU(cudaSetDevice(c->device));
 	cudaStream_t st = c->stream;
+	StreamOrder order(c, st);
 	for (int y = 0; y < h; ++y)
 		memcpy(c->h_block + (size_t) y * w * 4, rgba + (size_t) y * iw * 4, (size_t) w * 4);
 	uint8_t *d_px = (uint8_t *) c->small.p + 512, *d_out = d_px + 64;
@@ -773,6 +966,7 @@ int s2tc_b200_transcode_device(s2tc_b200_ctx *c, int dxt, void *d_blocks, size_t
 	std::lock_guard<std::mutex> lock(c->mu);
 	CU(cudaSetDevice(c->device));
 	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	StreamOrder order(c, st);
 	FamScope f(c, st, kFamTranscode, 1);
 	CU(launch_transcode(dxt, d_blocks, nblocks, st));
 	return 0;
@@ -810,6 +1004,7 @@ int s2tc_b200_decode_device(s2tc_b200_ctx *c, int dxt, const void *d_blocks, int
 	std::lock_guard<std::mutex> lock(c->mu);
 	CU(cudaSetDevice(c->device));
 	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	StreamOrder order(c, st);
 	FamScope f(c, st, kFamTranscode, 1);
 	CU(launch_decode(dxt, d_blocks, width, height, d_rgba, st));
 	return 0;

@@ -168,7 +168,9 @@ constexpr int kDitherSummaryLaunches = 3;                     // maps + two scan
 cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits, size_t npixels,
 		ByteMap *d_summary, void *d_workspace, cudaStream_t stream);
 
+// carry entering a range = the first `rank` summaries of d_maps (4 ByteMaps each) applied in order to a zero carry
 cudaError_t launch_fold_carry(const ByteMap *d_maps, int rank, int srccomps, int alphabits, int *d_carry, cudaStream_t stream);
+cudaError_t launch_identity_maps(ByteMap *d_maps, int count, int srccomps, int alphabits, cudaStream_t stream);
 
 // DITHER_FLOYDSTEINBERG over a whole width x height image (a 2-D recurrence: it cannot start in the middle)
 size_t floyd_workspace_bytes(int width, int height);

@@ -699,6 +699,21 @@ cudaError_t launch_fold_carry(const ByteMap *d_maps, int rank, int srccomps, int
 	return cudaGetLastError();
 }
 
+// `count` identity summaries (4 maps each): what an empty texel range contributes to a carry chain
+__global__ void identity_maps_kernel(ByteMap *maps, int count, ChanKinds kinds)
+{
+	for (int i = threadIdx.x; i < count * 4; i += blockDim.x)
+		bmap_identity(maps[i], kinds.k[i & 3]);
+}
+
+cudaError_t launch_identity_maps(ByteMap *d_maps, int count, int srccomps, int alphabits, cudaStream_t stream)
+{
+	if (count <= 0)
+		return cudaSuccess;
+	identity_maps_kernel<<<1, 128, 0, stream>>>(d_maps, count, chan_kinds(srccomps, alphabits));
+	return cudaGetLastError();
+}
+
 cudaError_t launch_prepass_simple(const void *d_src, int srccomps, int alphabits, size_t npixels, void *d_reduced,
 		int *d_carry, void *d_workspace, bool maps_ready, cudaStream_t stream)
 {

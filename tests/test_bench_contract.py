@@ -22,7 +22,9 @@ def test_reference_arm_line():
     assert d["impl"] == "reference" and d["metric"] == "encode_mblocks_per_s" and d["unit"] == "Mblocks/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
     assert d["value"] > 0 and d["ms_per_step"] > 0
-    assert "workload" in d["config"] and "DXT5" in d["config"]["workload"] and "SRGB_MIXED" in d["config"]["workload"]
+    # default = the north-star configuration (config 3), strong-scaled
+    assert "workload" in d["config"] and "DXT1" in d["config"]["workload"] and "S2TC_RANDOM_COLORS=64" in d["config"]["workload"]
+    assert d["scaling"] == "strong"
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     e = d["e2e"]
@@ -30,5 +32,5 @@ def test_reference_arm_line():
 
 
 def test_reference_arm_other_workload():
-    d = _run("--workload", "defaults")
-    assert "DXT1" in d["config"]["workload"] and "WAVG" in d["config"]["workload"] and d["value"] > 0
+    d = _run("--workload", "config2")
+    assert "DXT5" in d["config"]["workload"] and "SRGB_MIXED" in d["config"]["workload"] and d["value"] > 0
