@@ -138,6 +138,16 @@ int s2tc_b200_compress_mipchain_device(s2tc_b200_ctx *ctx, const s2tc_b200_setti
 		void *d_scratch, void *d_dst, uint64_t *rand_cursor, void *stream);
 int s2tc_b200_compress_mipchain_host(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int width, int height, const uint8_t *rgba,
 		uint8_t *dest, uint64_t *rand_cursor);
+/* A batch of ntex equally sized RGBA8 textures (back to back in d_rgba, not modified) under nset settings: every mip level
+ * of all textures goes through each kernel in ONE launch (the per-level kernels of a single chain are tiny from 64x64
+ * down), and the 565 pre-pass of a level is shared by the settings that agree on dither mode and alpha width.  The chain
+ * of texture i under setting k is written to d_dst + off_k + i*mipchain_bytes(dxt_k), where off_0 = 0 and
+ * off_{k+1} = off_k + ntex*mipchain_bytes(dxt_k) rounded up to a multiple of 16 (d_dst itself 16-byte aligned).
+ * Each texture is its own run of the reference tool: carries restart per level, every texture's rand() cursor starts
+ * at rand_cursor0.  d_scratch: ntex*(width*height + width*height/4) + 256 bytes.  (BASELINE config 4; the reference loop
+ * is s2tc_compress.c:722-733 once per file and per S2TC_COLORDIST_MODE.) */
+int s2tc_b200_compress_mipchain_batch_device(s2tc_b200_ctx *ctx, const s2tc_b200_settings *sets, int nset, int width, int height,
+		int ntex, const void *d_rgba, void *d_scratch, void *d_dst, uint64_t rand_cursor0, void *stream);
 
 /* ---- 565 pre-pass only: backs the exported rgb565_image (ref s2tc_algorithm.h:38) ------------- */
 int s2tc_b200_rgb565_host(s2tc_b200_ctx *ctx, uint8_t *out, const uint8_t *src, int width, int height, int srccomps,

@@ -144,6 +144,7 @@ def lib():
     L.s2tc_b200_mip_reduce_device.argtypes = [vp, vp, i32, i32, vp, vp]
     L.s2tc_b200_compress_mipchain_device.argtypes = [vp, sp, i32, i32, vp, vp, vp, C.POINTER(u64), vp]
     L.s2tc_b200_compress_mipchain_host.argtypes = [vp, sp, i32, i32, vp, vp, C.POINTER(u64)]
+    L.s2tc_b200_compress_mipchain_batch_device.argtypes = [vp, sp, i32, i32, i32, i32, vp, vp, vp, u64, vp]
     L.s2tc_b200_decode_device.argtypes = [vp, i32, vp, i32, i32, vp, vp]
     L.s2tc_b200_decode_host.argtypes = [vp, i32, vp, i32, i32, vp]
     L.s2tc_b200_rgb565_host.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32]
@@ -250,6 +251,13 @@ class Encoder:
         _check(lib().s2tc_b200_compress_mipchain_device(self._ctx, C.byref(s), width, height, _addr(rgba), _addr(scratch), _addr(dst),
                                                         C.byref(cur), stream))
         return cur.value
+
+    def compress_mipchain_batch_device(self, rgba, scratch, dst, width, height, ntex, settings_list, cursor0=0, stream=None):
+        """ntex textures back to back in `rgba` (device), every mip level of all of them per launch, once per entry of
+        settings_list; chains are written setting-major, texture-minor into `dst` (see include/s2tc_b200.h)."""
+        arr = (_Settings * len(settings_list))(*[s.c() for s in settings_list])
+        _check(lib().s2tc_b200_compress_mipchain_batch_device(self._ctx, arr, len(settings_list), width, height, ntex, _addr(rgba),
+                                                              _addr(scratch), _addr(dst), cursor0, stream))
 
     def rgb565_image(self, img, alphabits, dither):
         h, w, comps = img.shape

@@ -168,9 +168,19 @@ int settings_normalise(const s2tc_b200_settings *in, s2tc_b200_settings &s)
 int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &v, long long blk0, uint64_t cursor0,
 		void *d_dst, cudaStream_t st)
 {
-	const long long nblocks = (long long) v.blocks_w * v.blocks_h;
+	const long long nblocks = view_blocks(v);
 	if (nblocks == 0)
 		return 0;
+	if (v.images > 1 && s.nrandom > 0) { // the chunked rand() stream of the search kernel is per image: one image at a time
+		ImageView one = v;
+		one.images = 1;
+		for (int i = 0; i < v.images; ++i) {
+			one.base = v.base + (size_t) i * v.image_bytes;
+			if (int rc = encode_view(c, s, one, blk0, cursor0, (uint8_t *) d_dst + (size_t) i * v.out_image_bytes, st))
+				return rc;
+		}
+		return 0;
+	}
 	if (is_fast_mode(s.cd, s.nrandom)) {
 		FamScope f(c, st, kFamFast, 1);
 		CU(launch_fast_encode(s.dxt, s.cd, s.refine, v, d_dst, st));
@@ -859,6 +869,92 @@ int s2tc_b200_compress_mipchain_device(s2tc_b200_ctx *c, const s2tc_b200_setting
 	}
 	if (rand_cursor)
 		*rand_cursor = cursor;
+	return 0;
+}
+
+// A batch of equally sized textures, every mip level of all of them per launch (SURVEY "next" N2 / BASELINE config 4):
+// ntex RGBA8 textures back to back in d_rgba (not modified); for each of the nset settings the whole chain of every
+// texture is encoded.  The chain of texture i under setting k goes to
+//     d_dst + off_k + i * mipchain_bytes(dxt_k),   off_0 = 0,  off_{k+1} = (off_k + ntex * mipchain_bytes(dxt_k)) rounded up to 16.
+// d_scratch: ntex * (width*height + width*height/4) + 256 bytes (the two mip buffers).  Each texture is its own run of
+// the reference tool (s2tc_compress.c:722-733): the DITHER_SIMPLE carry restarts at every level and every texture's
+// rand() cursor starts at rand_cursor0.  The 565 pre-pass of a level is shared by all settings that agree on the dither
+// mode and the alpha width.  Launches per call: about levels * (6 + nset * 1..3), independent of ntex (nrandom <= 0).
+int s2tc_b200_compress_mipchain_batch_device(s2tc_b200_ctx *c, const s2tc_b200_settings *sets, int nset, int width, int height, int ntex,
+		const void *d_rgba, void *d_scratch, void *d_dst, uint64_t rand_cursor0, void *stream)
+{
+	if (!c || !sets || !d_rgba || !d_scratch || !d_dst)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	if (width <= 0 || height <= 0 || ntex <= 0 || nset <= 0)
+		return fail(S2TC_B200_EINVAL, "bad batch %d x %dx%d, %d settings", ntex, width, height, nset);
+	std::vector<s2tc_b200_settings> ss(nset);
+	std::vector<size_t> set_off(nset + 1, 0), chain(nset);
+	for (int k = 0; k < nset; ++k) {
+		if (int rc = settings_normalise(&sets[k], ss[k]))
+			return rc;
+		chain[k] = s2tc_b200_mipchain_bytes(ss[k].dxt, width, height);
+		set_off[k + 1] = (set_off[k] + chain[k] * ntex + 15) & ~(size_t) 15; // 16-byte blocks are stored with 128-bit stores
+	}
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	StreamOrder order(c, st);
+	const size_t level1 = (size_t) ntex * (width > 1 ? width >> 1 : width) * (height > 1 ? height >> 1 : height) * 4;
+	const uint8_t *cur = (const uint8_t *) d_rgba;
+	uint8_t *bufs[2] = {(uint8_t *) d_scratch, (uint8_t *) d_scratch + ((level1 + 255) & ~(size_t) 255)};
+	int *zero_carry = (int *) c->small.p + 16;
+	CU(cudaMemsetAsync(zero_carry, 0, 4 * sizeof(int), st));
+	std::vector<size_t> level_off(nset, 0);
+	std::vector<uint64_t> cursor(nset, rand_cursor0);
+	int flip = 0;
+	for (int w = width, h = height;;) {
+		const int bw = (w + 3) / 4, bh = (h + 3) / 4;
+		const size_t npix = (size_t) w * h;
+		int have_dither = -1, have_abits = -1; // what c->reduced currently holds for this level
+		for (int k = 0; k < nset; ++k) {
+			const s2tc_b200_settings &s = ss[k];
+			const int abits = alpha_bits(s.dxt), bs = block_bytes(s.dxt);
+			const uint8_t *texels = cur;
+			int fmt = kSrcRGBA8;
+			if (s.dither != kDitherNone) {
+				if (have_dither != s.dither || have_abits != abits) {
+					CU(c->reduced.reserve(npix * 4 * ntex));
+					if (s.dither == kDitherSimple) {
+						CU(c->dither_ws.reserve(dither_workspace_bytes(npix * ntex)));
+						FamScope f(c, st, kFamPrepass, prepass_simple_batch_launches(npix, ntex));
+						CU(launch_prepass_simple_batch(cur, 4, abits, npix, ntex, c->reduced.p, zero_carry, c->dither_ws.p, st));
+						if (npix > 16384 && npix % 16384)
+							CU(cudaMemsetAsync(zero_carry, 0, 4 * sizeof(int), st));
+					} else {
+						CU(c->dither_ws.reserve(floyd_workspace_bytes(w, h)));
+						FamScope f(c, st, kFamPrepass, ntex * 2);
+						for (int i = 0; i < ntex; ++i)
+							CU(launch_prepass_floyd(cur + (size_t) i * npix * 4, 4, abits, w, h, (uint8_t *) c->reduced.p + (size_t) i * npix * 4,
+									c->dither_ws.p, st));
+					}
+					have_dither = s.dither;
+					have_abits = abits;
+				}
+				texels = (const uint8_t *) c->reduced.p;
+				fmt = kSrcReduced;
+			}
+			const ImageView v = make_batch_view(texels, w, h, fmt, abits, ntex, npix * 4, chain[k]);
+			if (int rc = encode_view(c, s, v, 0, cursor[k], (uint8_t *) d_dst + set_off[k] + level_off[k], st))
+				return rc;
+			level_off[k] += (size_t) bw * bh * bs;
+			cursor[k] += (uint64_t) bw * bh * draws_per_block(s.dxt, s.nrandom);
+		}
+		if (w == 1 && h == 1)
+			break;
+		{
+			FamScope f(c, st, kFamPrepass, 1);
+			CU(launch_mip_reduce(cur, w, h, bufs[flip], st, ntex));
+		}
+		cur = bufs[flip];
+		flip ^= 1;
+		w = w > 1 ? w >> 1 : w;
+		h = h > 1 ? h >> 1 : h;
+	}
 	return 0;
 }
 

@@ -21,6 +21,10 @@ struct ImageView {
 	int alphabits; // 1 / 4 / 8, used when fmt is a raw format (fused DITHER_NONE)
 	int blocks_w;  // ceil(width / 4)
 	int blocks_h;  // ceil(rows / 4)
+	// a batch of `images` equally sized images (mip levels of many textures): image k starts image_bytes * k after base
+	// and its blocks go out_image_bytes * k after the output base; 1 image for everything else
+	int images;
+	size_t image_bytes, out_image_bytes;
 };
 
 inline ImageView make_view(const void *base, int width, int rows, int fmt, int alphabits)
@@ -33,10 +37,39 @@ inline ImageView make_view(const void *base, int width, int rows, int fmt, int a
 	v.alphabits = alphabits;
 	v.blocks_w = (width + 3) / 4;
 	v.blocks_h = (rows + 3) / 4;
+	v.images = 1;
+	v.image_bytes = v.out_image_bytes = 0;
 	return v;
 }
 
+inline ImageView make_batch_view(const void *base, int width, int rows, int fmt, int alphabits, int images, size_t image_bytes,
+		size_t out_image_bytes)
+{
+	ImageView v = make_view(base, width, rows, fmt, alphabits);
+	v.images = images;
+	v.image_bytes = image_bytes;
+	v.out_image_bytes = out_image_bytes;
+	return v;
+}
+
+inline long long view_blocks(const ImageView &v) { return (long long) v.blocks_w * v.blocks_h * v.images; }
+
 #if defined(__CUDACC__)
+// Block number t of a (possibly batched) view: moves v to the image that holds it, returns the block's number inside that
+// image and, in out_off, where that image's blocks start in the output.
+__device__ __forceinline__ int select_image(ImageView &v, int t, size_t &out_off)
+{
+	out_off = 0;
+	if (v.images > 1) {
+		const int per = v.blocks_w * v.blocks_h;
+		const int img = t / per;
+		t -= img * per;
+		v.base += (size_t) img * v.image_bytes;
+		out_off = (size_t) img * v.out_image_bytes;
+	}
+	return t;
+}
+
 // fused DITHER_NONE on a raw RGBA word (ref s2tc_algorithm.cpp:1274-1297)
 __device__ __forceinline__ uint32_t reduce_word(uint32_t w, int alphabits)
 {
@@ -163,6 +196,11 @@ size_t dither_workspace_bytes(size_t npixels);
 cudaError_t launch_prepass_simple(const void *d_src, int srccomps, int alphabits, size_t npixels, void *d_reduced,
 		int *d_carry, void *d_workspace, bool maps_ready, cudaStream_t stream);
 int prepass_simple_launches(size_t npixels, bool maps_ready); // kernel launches the call above makes
+// `images` images of npixels texels each, back to back, each from carry 0; d_zero_carry: 4 zeroed ints of scratch;
+// workspace: dither_workspace_bytes(npixels * images)
+cudaError_t launch_prepass_simple_batch(const void *d_src, int srccomps, int alphabits, size_t npixels, int images, void *d_reduced,
+		int *d_zero_carry, void *d_workspace, cudaStream_t stream);
+int prepass_simple_batch_launches(size_t npixels, int images);
 constexpr int kDitherSummaryLaunches = 3;                     // maps + two scan launches
 // transfer maps only (for sharding a carry chain across GPUs): d_summary receives 4 ByteMaps
 cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits, size_t npixels,
@@ -177,8 +215,9 @@ size_t floyd_workspace_bytes(int width, int height);
 cudaError_t launch_prepass_floyd(const void *d_src, int srccomps, int alphabits, int width, int height, void *d_reduced,
 		void *d_workspace, cudaStream_t stream);
 
-// one mip step of an RGBA8 image (w x h -> max(w/2,1) x max(h/2,1)); d_out must not alias d_in
-cudaError_t launch_mip_reduce(const void *d_in, int w, int h, void *d_out, cudaStream_t stream);
+// one mip step of `images` RGBA8 images stored back to back (w x h -> max(w/2,1) x max(h/2,1) each, results back to back);
+// d_out must not alias d_in
+cudaError_t launch_mip_reduce(const void *d_in, int w, int h, void *d_out, cudaStream_t stream, int images = 1);
 
 // S2TC decode of a whole image to RGBA8 (tightly packed blocks in, width*height*4 bytes out)
 cudaError_t launch_decode(int dxt, const void *d_blocks, int width, int height, void *d_rgba, cudaStream_t stream);

@@ -15,11 +15,13 @@ namespace s2tc {
 template <int DXT, int CD>
 __global__ void __launch_bounds__(128) fast_encode_kernel(ImageView v, int refine, uint8_t *out)
 {
-	const int nblocks = v.blocks_w * v.blocks_h;
+	const int nblocks = v.blocks_w * v.blocks_h * v.images;
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= nblocks)
 		return;
-	const int by = t / v.blocks_w, bx = t - by * v.blocks_w;
+	size_t out_off;
+	const int ti = select_image(v, t, out_off);
+	const int by = ti / v.blocks_w, bx = ti - by * v.blocks_w;
 	Block b;
 	load_block(v, bx, by, b);
 	uint32_t c0, c1;
@@ -28,15 +30,15 @@ __global__ void __launch_bounds__(128) fast_encode_kernel(ImageView v, int refin
 	uint32_t w[4];
 	finish_block<DXT, CD>(b, refine, c0, c1, a0, a1, w);
 	if (DXT == kDxt1)
-		reinterpret_cast<uint2 *>(out)[t] = make_uint2(w[0], w[1]);
+		reinterpret_cast<uint2 *>(out + out_off)[ti] = make_uint2(w[0], w[1]);
 	else
-		reinterpret_cast<uint4 *>(out)[t] = make_uint4(w[0], w[1], w[2], w[3]);
+		reinterpret_cast<uint4 *>(out + out_off)[ti] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 template <int DXT>
 static cudaError_t launch_fast_dxt(int cd, int refine, const ImageView &v, void *d_out, cudaStream_t stream)
 {
-	const int nblocks = v.blocks_w * v.blocks_h;
+	const int nblocks = (int) view_blocks(v);
 	if (nblocks == 0)
 		return cudaSuccess;
 	const dim3 block(128), grid((nblocks + 127) / 128);

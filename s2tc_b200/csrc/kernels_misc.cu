@@ -312,8 +312,13 @@ __device__ __forceinline__ void scan_load_warp_tiles(const ByteMap *__restrict__
 	__syncwarp();
 }
 
+// tiles_per_image > 0: the texel stream is a batch of images of that many tiles each and the carry restarts at every
+// image (each mip level of each texture is its own tx_compress_dxtn call, ref s2tc_compress.c:722-733).  A restart is
+// the constant map "everything -> carry 0", so it composes like any other map; only the 1-bit alpha channel, whose map
+// is a sum, needs a flag (byte 1 of its partial map: the part contains a restart and byte 0 counts from there).
 __global__ void __launch_bounds__(kScanCtaWarps * 32)
-scan_partial_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKinds kinds, uint8_t *__restrict__ parts /* [warps][4][32] */)
+scan_partial_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKinds kinds, uint8_t *__restrict__ parts /* [warps][4][32] */,
+		unsigned tiles_per_image)
 {
 	__shared__ __align__(16) uint8_t s_tiles[kScanCtaWarps][kScanWarpTiles][4][32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -327,12 +332,19 @@ scan_partial_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKin
 #pragma unroll
 	for (int ch = 0; ch < 4; ++ch)
 		acc[ch] = kinds.k[ch] == kChanBit1 ? 0u : (uint32_t) lane;
+	bool restarted = false;
 	for (int i = 0; i < cnt; ++i) {
+		const bool restart = tiles_per_image && (tile0 + i) % tiles_per_image == 0;
+		restarted |= restart;
 #pragma unroll
 		for (int ch = 0; ch < 4; ++ch) {
-			if (kinds.k[ch] <= kChanShift4)
+			if (kinds.k[ch] <= kChanShift4) {
+				if (restart)
+					acc[ch] = (uint32_t) chan_radius(kinds.k[ch]);
 				acc[ch] = s_tiles[warp][i][ch][acc[ch]]; // out[k] = tile[acc[k]]
-			else if (kinds.k[ch] == kChanBit1) {
+			} else if (kinds.k[ch] == kChanBit1) {
+				if (restart)
+					acc[ch] = 0;
 				acc[ch] += s_tiles[warp][i][ch][0];
 				acc[ch] = acc[ch] >= 255u ? acc[ch] - 255u : acc[ch];
 			}
@@ -340,7 +352,7 @@ scan_partial_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKin
 	}
 #pragma unroll
 	for (int ch = 0; ch < 4; ++ch)
-		parts[(gw * 4 + ch) * 32 + lane] = (uint8_t) acc[ch];
+		parts[(gw * 4 + ch) * 32 + lane] = kinds.k[ch] == kChanBit1 && lane == 1 ? (uint8_t) restarted : (uint8_t) acc[ch];
 }
 
 __global__ void __launch_bounds__(128)
@@ -375,6 +387,8 @@ scan_carry_kernel(const uint8_t *__restrict__ parts, size_t nparts, ChanKinds ki
 			for (int i = 0; i < cnt; ++i) {
 				if (!summary && lane == 0)
 					starts[(base + i) * 4 + ch] = (int) v - 127;
+				if (s_parts[i][ch][1]) // the part contains a restart: its sum counts from carry 0
+					v = summary ? 0u : 127u;
 				v += s_parts[i][ch][0];
 				v = v >= 255u ? v - 255u : v;
 			}
@@ -392,7 +406,7 @@ scan_carry_kernel(const uint8_t *__restrict__ parts, size_t nparts, ChanKinds ki
 
 __global__ void __launch_bounds__(kScanCtaWarps * 32)
 scan_walk_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKinds kinds, const int *__restrict__ starts,
-		int *__restrict__ tile_carry)
+		int *__restrict__ tile_carry, unsigned tiles_per_image)
 {
 	__shared__ __align__(16) uint8_t s_tiles[kScanCtaWarps][kScanWarpTiles][4][32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -410,6 +424,8 @@ scan_walk_kernel(const ByteMap *__restrict__ tilemaps, size_t ntiles, ChanKinds 
 		uint32_t v = kind <= kChanShift4 ? (uint32_t) (c0 + r) : (uint32_t) (c0 + 127);
 		for (int i = 0; i < cnt; ++i) {
 			int c = 0;
+			if (tiles_per_image && (tile0 + i) % tiles_per_image == 0)
+				v = kind <= kChanShift4 ? (uint32_t) r : 127u; // a new image: carry 0
 			if (kind <= kChanShift4) {
 				c = (int) v - r;
 				v = s_tiles[warp][i][ch][v & 31u];
@@ -548,8 +564,11 @@ dither_apply_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits
 // which dominated mip chains (12 levels per texture).
 __global__ void __launch_bounds__(kTileThreads)
 dither_small_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits, ChanKinds kinds, int npixels,
-		const DitherLut *__restrict__ lut, int *carry /* 4 ints in/out */, uint32_t *__restrict__ out)
+		const DitherLut *__restrict__ lut, int *carry /* 4 ints in/out; NULL: zero in, nothing out */, uint32_t *__restrict__ out)
 {
+	// one CTA per image of a batch (images back to back, npixels each)
+	src += (size_t) blockIdx.x * npixels * srccomps;
+	out += (size_t) blockIdx.x * npixels;
 	__shared__ __align__(16) uint32_t s_lut3[256][4];
 	__shared__ __align__(16) uint32_t s_lut2[256];
 	__shared__ ByteMap s_maps[kTileThreads * 4];
@@ -591,7 +610,9 @@ dither_small_kernel(const uint8_t *__restrict__ src, int srccomps, int alphabits
 	__syncthreads();
 	if ((t & 31) == 0) {
 		const int ch = t >> 5;
-		carry[ch] = walk_chunk_carries(s_maps, s_carry, ch, kinds.k[ch], carry[ch]);
+		const int cout = walk_chunk_carries(s_maps, s_carry, ch, kinds.k[ch], carry ? carry[ch] : 0);
+		if (carry)
+			carry[ch] = cout;
 	}
 	__syncthreads();
 	int cc[4] = {s_carry[t * 4 + 0], s_carry[t * 4 + 1], s_carry[t * 4 + 2], s_carry[t * 4 + 3]};
@@ -643,7 +664,7 @@ static const DitherLut *device_dither_lut(cudaError_t *err)
 
 // phases: 1 = chunk/tile maps, 2 = scan (+ summary), 4 = apply; any combination, in order
 static cudaError_t run_dither(int phases, const void *d_src, int srccomps, int alphabits, size_t npixels, void *d_reduced,
-		int *d_carry, ByteMap *d_summary, void *d_workspace, cudaStream_t stream)
+		int *d_carry, ByteMap *d_summary, void *d_workspace, cudaStream_t stream, unsigned tiles_per_image = 0)
 {
 	if (!npixels)
 		return cudaSuccess;
@@ -670,10 +691,10 @@ static cudaError_t run_dither(int phases, const void *d_src, int srccomps, int a
 		static_assert(kScanWarpTiles == 32, "scan_parts_count");
 		const size_t nparts = scan_parts_count(tiles);
 		const unsigned ctas = (unsigned) ((tiles + kScanCtaTiles - 1) / kScanCtaTiles);
-		scan_partial_kernel<<<ctas, kScanCtaWarps * 32, 0, stream>>>(tilemaps, tiles, kinds, scan_parts);
+		scan_partial_kernel<<<ctas, kScanCtaWarps * 32, 0, stream>>>(tilemaps, tiles, kinds, scan_parts, tiles_per_image);
 		scan_carry_kernel<<<1, 128, 0, stream>>>(scan_parts, nparts, kinds, d_carry, scan_starts, d_summary);
 		if (!d_summary)
-			scan_walk_kernel<<<ctas, kScanCtaWarps * 32, 0, stream>>>(tilemaps, tiles, kinds, scan_starts, tile_carry);
+			scan_walk_kernel<<<ctas, kScanCtaWarps * 32, 0, stream>>>(tilemaps, tiles, kinds, scan_starts, tile_carry, tiles_per_image);
 	}
 	if (phases & 4)
 		dither_apply_kernel<<<(unsigned) tiles, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, alphabits,
@@ -718,6 +739,48 @@ cudaError_t launch_prepass_simple(const void *d_src, int srccomps, int alphabits
 		int *d_carry, void *d_workspace, bool maps_ready, cudaStream_t stream)
 {
 	return run_dither(maps_ready ? 6 : 7, d_src, srccomps, alphabits, npixels, d_reduced, d_carry, nullptr, d_workspace, stream);
+}
+
+// DITHER_SIMPLE over `images` images of npixels texels each, stored back to back, every image starting from carry 0 (a
+// batch of tx_compress_dxtn calls).  Small images: one fused CTA each, one launch; images of whole tiles: the ordinary
+// three phases over the concatenated texels with the carry restarting at image boundaries; any other size: image by image.
+// d_zero_carry: 4 ints that are zero (and stay zero only in the first two cases; the third rewrites them per image).
+int prepass_simple_batch_launches(size_t npixels, int images)
+{
+	if (!npixels || images <= 0)
+		return 0;
+	if (npixels <= (size_t) kTilePixels)
+		return 1;
+	return npixels % kTilePixels == 0 ? 5 : 6 * images;
+}
+
+cudaError_t launch_prepass_simple_batch(const void *d_src, int srccomps, int alphabits, size_t npixels, int images, void *d_reduced,
+		int *d_zero_carry, void *d_workspace, cudaStream_t stream)
+{
+	if (!npixels || images <= 0)
+		return cudaSuccess;
+	const ChanKinds kinds = chan_kinds(srccomps, alphabits);
+	if (npixels <= (size_t) kTilePixels) {
+		cudaError_t e;
+		const DitherLut *lut = device_dither_lut(&e);
+		if (!lut)
+			return e;
+		dither_small_kernel<<<images, kTileThreads, 0, stream>>>((const uint8_t *) d_src, srccomps, alphabits, kinds, (int) npixels, lut,
+				nullptr, (uint32_t *) d_reduced);
+		return cudaGetLastError();
+	}
+	if (npixels % kTilePixels == 0)
+		return run_dither(7, d_src, srccomps, alphabits, npixels * images, d_reduced, d_zero_carry, nullptr, d_workspace, stream,
+				(unsigned) (npixels / kTilePixels));
+	for (int i = 0; i < images; ++i) {
+		cudaError_t e = cudaMemsetAsync(d_zero_carry, 0, 4 * sizeof(int), stream);
+		if (e == cudaSuccess)
+			e = run_dither(7, (const uint8_t *) d_src + (size_t) i * npixels * srccomps, srccomps, alphabits, npixels,
+					(uint32_t *) d_reduced + (size_t) i * npixels, d_zero_carry, nullptr, d_workspace, stream);
+		if (e != cudaSuccess)
+			return e;
+	}
+	return cudaSuccess;
 }
 
 cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits, size_t npixels, ByteMap *d_summary,
@@ -858,13 +921,14 @@ cudaError_t launch_transcode(int dxt, void *d_blocks, size_t nblocks, cudaStream
 // every axis still larger than 1 is halved, odd sizes drop the last row/column, texels are the truncated
 // mean of the 2x2 (or 2x1 / 1x2) source texels per channel.  One thread per output texel, 32-bit loads.
 // =====================================================================================================
-__global__ void mip_reduce_kernel(const uint32_t *__restrict__ in, int w, int h, uint32_t *__restrict__ out, int nw, int nh)
+__global__ void mip_reduce_kernel(const uint32_t *__restrict__ in, int w, int h, uint32_t *__restrict__ out, int nw, int nh, int images)
 {
 	const int sx = w > 1 ? 2 : 1, sy = h > 1 ? 2 : 1;
-	const size_t n = (size_t) nw * nh, stride = (size_t) gridDim.x * blockDim.x;
+	const size_t per = (size_t) nw * nh, n = per * images, stride = (size_t) gridDim.x * blockDim.x;
 	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-		const int y = (int) (i / nw), x = (int) (i - (size_t) y * nw);
-		const uint32_t *p = in + (size_t) y * sy * w + (size_t) x * sx;
+		const size_t img = i / per, r = i - img * per;
+		const int y = (int) (r / nw), x = (int) (r - (size_t) y * nw);
+		const uint32_t *p = in + img * ((size_t) w * h) + (size_t) y * sy * w + (size_t) x * sx;
 		const uint32_t a = __ldg(p), b = sx == 2 ? __ldg(p + 1) : 0u;
 		const uint32_t c = sy == 2 ? __ldg(p + w) : 0u, d = (sx == 2 && sy == 2) ? __ldg(p + w + 1) : 0u;
 		const int sh = (sx == 2) + (sy == 2);
@@ -875,17 +939,17 @@ __global__ void mip_reduce_kernel(const uint32_t *__restrict__ in, int w, int h,
 	}
 }
 
-cudaError_t launch_mip_reduce(const void *d_in, int w, int h, void *d_out, cudaStream_t stream)
+cudaError_t launch_mip_reduce(const void *d_in, int w, int h, void *d_out, cudaStream_t stream, int images)
 {
 	const int nw = w > 1 ? w >> 1 : w, nh = h > 1 ? h >> 1 : h;
-	const size_t n = (size_t) nw * nh;
+	const size_t n = (size_t) nw * nh * images;
 	if (!n || (nw == w && nh == h))
 		return cudaSuccess;
 	const int threads = 256;
 	size_t blocks = (n + threads - 1) / threads;
 	if (blocks > 148 * 32)
 		blocks = 148 * 32;
-	mip_reduce_kernel<<<(unsigned) blocks, threads, 0, stream>>>((const uint32_t *) d_in, w, h, (uint32_t *) d_out, nw, nh);
+	mip_reduce_kernel<<<(unsigned) blocks, threads, 0, stream>>>((const uint32_t *) d_in, w, h, (uint32_t *) d_out, nw, nh, images);
 	return cudaGetLastError();
 }
 

@@ -406,11 +406,13 @@ constexpr int kSearch16Threads = 128;
 template <int DXT, int CD, bool COLOR, bool ALPHA>
 __global__ void __launch_bounds__(kSearch16Threads, S2TC_SEARCH16_MINBLOCKS) search16_kernel(ImageView v, uint32_t one, uint2 *__restrict__ ends)
 {
-	const int nblocks = v.blocks_w * v.blocks_h;
+	const int nblocks = v.blocks_w * v.blocks_h * v.images;
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= nblocks)
 		return;
-	const int by = t / v.blocks_w, bx = t - by * v.blocks_w;
+	size_t out_off; // endpoints are indexed by the block's number in the whole batch
+	const int ti = select_image(v, t, out_off);
+	const int by = ti / v.blocks_w, bx = ti - by * v.blocks_w;
 	Block b;
 	load_block(v, bx, by, b);
 
@@ -454,7 +456,7 @@ static void launch_search16_cd(dim3 grid, dim3 block, const ImageView &v, uint2 
 template <int DXT>
 static cudaError_t launch_search16_dxt(int cd, const ImageView &v, uint2 *d_ends, cudaStream_t stream)
 {
-	const int nblocks = v.blocks_w * v.blocks_h;
+	const int nblocks = (int) view_blocks(v);
 	if (nblocks == 0)
 		return cudaSuccess;
 	const dim3 block(kSearch16Threads), grid((nblocks + kSearch16Threads - 1) / kSearch16Threads);
