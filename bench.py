@@ -443,6 +443,27 @@ def run_texture(args, wl, world, rank, local, dist):
     ms_e2e = float(t_e2e.item()) / args.steps
     e2e_value = total_blocks / (ms_e2e * 1e-3) / 1e6
 
+    # what the copies alone cost on this box: every rank moves its step's bytes (pinned host <-> device, both directions
+    # at once, no kernels) at the same time; an end-to-end step cannot be shorter than this
+    copy_only = None
+    if e2e_steps:
+        s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            with torch.cuda.stream(s_up):
+                d_src.copy_(h_src, non_blocking=True)
+            with torch.cuda.stream(s_down):
+                h_dst.copy_(d_dst, non_blocking=True)
+        barrier()
+        t_c = torch.tensor([(time.perf_counter() - t0) * 1e3 / 3], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+        ms_c = float(t_c.item())
+        copy_only = {"ms_per_step": ms_c, "h2d_gbs_all_gpus": width * height * 4 / (ms_c * 1e-3) / 1e9,
+                     "note": "pinned H2D of every rank's texels and D2H of its blocks, all ranks at once, no kernels: the floor of "
+                             "an end-to-end step on this host"}
+
     # the entry point a drop-in user calls, with the memory they pass: tx_compress_dxtn on malloc'd (pageable) buffers
     pageable = None
     if world == 1 and e2e_steps:
@@ -498,31 +519,37 @@ def run_texture(args, wl, world, rank, local, dist):
         # -- one warp instruction per scheduler and clock; a 32-bit min or add is one operation per lane, a packed 16-bit one
         # is two -- at the SM clock of MEASURED_PEAKS.json; the rates the kernels' own instruction mixes sustain in a
         # micro-benchmark of this run are reported beside it.
+        # Per-block figure = SURVEY.md 8(d)'s: every block has n = 16 colours, m = 16 + nrandom candidates.  What the reference
+        # would really execute on THIS texture (fewer colours in partly transparent DXT1 blocks) is reported beside it.
+        nom16, nom32 = search_ops(np.bincount([16], minlength=17), nrandom, st.dxt, cd_n)
         red = enc.rgb565_image(mine, abits, st.dither) if st.dxt == 0 else None
         hist = gathered_counts(red if red is not None else mine, st.dxt)
-        ops16, ops32 = search_ops(hist, nrandom, st.dxt, cd_n)
-        nom16, nom32 = search_ops(np.bincount([16], minlength=17), nrandom, st.dxt, cd_n)
+        act16, act32 = search_ops(hist, nrandom, st.dxt, cd_n)
         r32 = sms * 128 * sm_mhz * 1e6 / 1e9           # Gop/s, scalar
         r16 = 2 * r32                                   # two 16-bit lanes per register
-        ops = ops16 + ops32
-        peak = ops / (ops32 / r32 + ops16 / r16)
+        ops = nom16 + nom32
+        peak = ops / (nom32 / r32 + nom16 / r16)
         s_launch_group = 2 if (nrandom <= 0 and st.dxt == 2) else 1
         s_groups = max(fam["search"][1] // s_launch_group, 1)
         s_ms = fam["search"][0] / s_groups
         s_blocks = my_blocks * args.steps / s_groups
         achieved = ops * s_blocks / (s_ms * 1e-3) / 1e9
+        act = act16 + act32
+        act_peak = act / (act32 / r32 + act16 / r16)
+        act_achieved = act * s_blocks / (s_ms * 1e-3) / 1e9
         peak_scalar, peak_packed = enc.int_peaks_gops()
         roofline = {"bound": "int32", "kernel": "pair_search_kernel" if nrandom > 0 else "search16_kernel",
                     "achieved": achieved, "peak": peak, "unit": "Gop/s", "frac": achieved / peak,
                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
                     "ms_per_launch": s_ms, "blocks_per_launch": s_blocks,
-                    "ops_per_block": ops, "ops_per_block_16bit_packed": ops16, "ops_per_block_32bit": ops32,
-                    "ops_per_block_if_every_block_had_16_colours": nom16 + nom32,
-                    "ops_definition": "reference algorithm on this texture: 2 per (pair, texel) for colours (+ the same for DXT5 "
-                                      "alpha) + distance evaluations of the matrix fill; n per block from the reduced texels",
-                    "note": "the pruned scan executes far fewer operations than the algorithm defines (pairs whose lower bound "
-                            "exceeds the best sum are never evaluated), so this is algorithmic work per second, not pipe occupancy"
-                            if nrandom > 0 else None,
+                    "ops_per_block": ops, "ops_per_block_16bit_packed": nom16, "ops_per_block_32bit": nom32,
+                    "ops_definition": "SURVEY.md 8(d): 2 per (pair, texel) over P = m(m-1)/2 pairs and n = 16 texels for colours (+ the "
+                                      "same for DXT5 alpha, fixed points folded) + D distance evaluations x C_cd of the matrix fill",
+                    "on_this_texture": {"ops_per_block": act, "achieved": act_achieved, "peak": act_peak, "frac": act_achieved / act_peak,
+                                        "note": "the reference's operation count with the n it really gathers per block (DXT1 skips "
+                                                "transparent texels; single-colour blocks cost it the same pairs but n columns)"},
+                    "note": "algorithmic work per second, not pipe occupancy: the pruned scan never evaluates pairs whose lower bound "
+                            "exceeds the best sum, and answers single-colour blocks at once" if nrandom > 0 else None,
                     "peak_source": f"issue ceiling: {sms} SMs x 128 lanes x {sm_mhz:.0f} MHz (x2 for packed 16-bit operands)",
                     "measured_mix_rates": {"scalar_gops": peak_scalar, "packed16_gops": peak_packed,
                                            "how": "s2tc_b200_int_peaks in this run: VIMNMX + IMAD; VIMNMX.U16x2 + IDP.2A"},
@@ -558,7 +585,7 @@ def run_texture(args, wl, world, rank, local, dist):
                 "path": "s2tc_b200_compress_host (what tx_compress_dxtn calls), pinned host buffers" if world == 1
                 else "s2tc_b200_compress_host_shard per rank (slab-pipelined H2D / kernels / D2H, one all-gather of the "
                      "DITHER_SIMPLE summaries), pinned host buffers",
-                "pageable": pageable},
+                "copy_only": copy_only, "pageable": pageable},
         "gpu_launches": launches, "clocks": clocks,
         "checked_blocks_vs_oracle": checked,
     }

@@ -157,6 +157,21 @@ def run(args, wl, world, rank, local, dist, ClockSampler, read_peaks, workload_c
     if dist is not None:
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     ms_e2e = float(t_e2e.item()) / args.steps
+    copy_only = None
+    if e2e_steps:      # the copies alone, all ranks at once: the floor of an end-to-end step on this host
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            with torch.cuda.stream(up):
+                d_src.copy_(h_src, non_blocking=True)
+            with torch.cuda.stream(down):
+                h_dst.copy_(d_dst, non_blocking=True)
+        barrier()
+        t_c = torch.tensor([(time.perf_counter() - t0) * 1e3 / 2], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+        copy_only = {"ms_per_step": float(t_c.item()),
+                     "note": "pinned H2D of the textures and D2H of the chains of every rank at once, no kernels"}
     if rank != 0:
         return None
 
@@ -192,7 +207,8 @@ def run(args, wl, world, rank, local, dist, ClockSampler, read_peaks, workload_c
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": blocks_step * world / (ms_e2e * 1e-3) / 1e6, "unit": "Mblocks/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": ntex * width * height * 4, "d2h_bytes_per_step": chain * ntex * len(sets),
-                "path": f"pinned host textures -> sub-batches of {SUB} (upload / batch encode / download overlapped) -> pinned host chains"},
+                "path": f"pinned host textures -> sub-batches of {SUB} (upload / batch encode / download overlapped) -> pinned host chains",
+                "copy_only": copy_only},
         "gpu_launches": launches, "launches_per_step": launches / args.steps, "clocks": clocks,
         "blocks_per_step_per_gpu": blocks_step, "checked_blocks_vs_oracle": checked,
     }
