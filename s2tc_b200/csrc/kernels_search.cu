@@ -30,7 +30,17 @@ constexpr int kSearchThreads = 32; // one warp per CTA: a CTA slot frees as soon
 constexpr int kSearchWarps = kSearchThreads / 32;
 constexpr int kPitch16 = 8;  // words per row, 16-bit distances: rows are only read whole (quantisation, exact sums of survivors)
 constexpr int kPitch32 = 20; // words per row, 32-bit distances (16 used)
-constexpr int kListCap = 288; // survivors waiting for their exact sum: < 32 carried over + at most 256 from one tile
+constexpr int kListCap = 288; // survivor groups waiting for their exact sums: < 8 carried over + at most 128 from one pass of two tile columns
+constexpr uint32_t kFlushGroups = 8; // 8 groups = 32 pairs = one exact sum per lane
+#ifndef S2TC_PS_FLUSH
+#define S2TC_PS_FLUSH 0
+#endif
+#ifndef S2TC_PS_TWOCOL
+#define S2TC_PS_TWOCOL 0
+#endif
+#ifndef S2TC_PS_MINCTAS
+#define S2TC_PS_MINCTAS 32
+#endif
 constexpr int kRing = 256;    // rand() outputs kept per warp (a batch of 32 candidates needs <= 128 + 61)
 
 template <int CD> struct Packs16 { static constexpr bool value = CD == kAVG || CD == kWAVG || CD == kW0AVG; };
@@ -279,9 +289,74 @@ __device__ __forceinline__ uint32_t pruned_search(const uint32_t *rows, uint4 *q
 		cneg[r] = kBoundBias - sad_row(q, make_uint4(0u, 0u, 0u, 0u), 0u);
 	}
 	__syncwarp();
-	// 2./3. bound scan; survivors to the list, exact evaluation in batches
+	// 2./3. bound scan; survivors to the list, exact evaluation in batches.  The list holds GROUPS of four pairs
+	// (i .. i+3, j) that share one test: a lane that finds a group appends one word with one atomic, and the flush sums
+	// all four pairs of every listed group exactly, one pair per lane (the ones that did not survive cost nothing -- the
+	// lanes would be idle -- and cannot win: their bound, hence their sum, is above T).  Round 2a appended pair by pair:
+	// four compiler-aggregated atomics per event, ~540 instructions per block in the survivor path (ncu source view).
 	uint32_t tq2 = (best.sum >> s) * 2u;
 	bool pending = false; // this lane has appended since the list was last emptied
+	auto append = [&](uint32_t top, int thr, bool jok, int ig, int j) {
+		if ((int) top >= thr && jok && ig < j) {
+			list[atomicAdd(cnt, 1u)] = ((uint32_t) ig << 16) | (uint32_t) j;
+			pending = true;
+		}
+	};
+	auto flush_if = [&](bool last_of_column, bool last_of_all) {
+		if (__any_sync(0xFFFFFFFFu, pending)) {
+			__syncwarp();
+			const uint32_t c = *cnt;
+			// S2TC_PS_FLUSH 0: at every column end (T as fresh as possible); 1: after the first column, at the end, and
+			// whenever 32 pairs are waiting
+			const bool now = c >= kFlushGroups || (S2TC_PS_FLUSH == 0 ? last_of_column : last_of_all);
+			if (now) {
+				__syncwarp(); // every lane has read the count
+				if (lane == 0)
+					*cnt = 0;
+				for (uint32_t idx = lane; idx < 4u * c; idx += 32) {
+					const uint32_t p = list[idx >> 2] + ((idx & 3u) << 16);
+					const int i = (int) (p >> 16), j = (int) (p & 0xFFFFu);
+					if (i < j)
+						best.take(exact_pair_sum<PACK16>(rows, i, j), p);
+				}
+				best.warp_min();
+				tq2 = (best.sum >> s) * 2u;
+				pending = false;
+				__syncwarp(); // list consumed and count reset before anyone appends again
+			}
+		}
+	};
+#if S2TC_PS_TWOCOL
+	// two tile columns per pass over the rows i: every broadcast row load meets two rows j
+	for (int b = 0; b < ntile; b += 2) {
+		const bool has1 = b + 1 < ntile; // warp-uniform
+		const int j0 = 16 * b + jj, j1 = has1 ? j0 + 16 : j0;
+		const uint4 r0 = q8[j0], r1 = q8[j1];
+		const uint32_t rqk0 = 2u * kBoundBias - cneg[j0], rqk1 = 2u * kBoundBias - cneg[j1]; // K + Rq[j]
+		const bool jok0 = j0 < m, jok1 = has1 && j1 < m;
+		const int alast = has1 ? b + 1 : b;
+		for (int a = 0; a <= alast; ++a) {
+			const int i0 = 16 * a + 8 * half;
+			const int thr0 = (int) (rqk0 - tq2), thr1 = (int) (rqk1 - tq2);
+			const uint4 *qi = q8 + i0;
+			const bool do0 = a <= b; // warp-uniform: column b has no tile below its diagonal
+#pragma unroll
+			for (int g = 0; g < 8; g += 4) {
+				const uint4 cc = *reinterpret_cast<const uint4 *>(cneg + i0 + g);
+				const uint4 x0 = qi[g], x1 = qi[g + 1], x2 = qi[g + 2], x3 = qi[g + 3];
+				if (do0) {
+					const uint32_t t0 = sad_row(x0, r0, cc.x), t1 = sad_row(x1, r0, cc.y), t2 = sad_row(x2, r0, cc.z), t3 = sad_row(x3, r0, cc.w);
+					append(max(max(t0, t1), max(t2, t3)), thr0, jok0, i0 + g, j0);
+				}
+				if (has1) {
+					const uint32_t t0 = sad_row(x0, r1, cc.x), t1 = sad_row(x1, r1, cc.y), t2 = sad_row(x2, r1, cc.z), t3 = sad_row(x3, r1, cc.w);
+					append(max(max(t0, t1), max(t2, t3)), thr1, jok1, i0 + g, j1);
+				}
+			}
+			flush_if(a == alast, a == alast && (b == 0 || b + 2 >= ntile));
+		}
+	}
+#else
 	for (int b = 0; b < ntile; ++b) {
 		const int j = 16 * b + jj;
 		const uint4 rj = q8[j];
@@ -302,36 +377,12 @@ __device__ __forceinline__ uint32_t pruned_search(const uint32_t *rows, uint4 *q
 			acc[6] = sad_row(qi[6], rj, cb.z);
 			acc[7] = sad_row(qi[7], rj, cb.w);
 #pragma unroll
-			for (int g = 0; g < 8; g += 4) {
-				const uint32_t top = max(max(acc[g], acc[g + 1]), max(acc[g + 2], acc[g + 3]));
-				if ((int) top >= thr && jok) {
-#pragma unroll
-					for (int t = g; t < g + 4; ++t)
-						if ((int) acc[t] >= thr && i0 + t < j) {
-							list[atomicAdd(cnt, 1u)] = ((uint32_t) (i0 + t) << 16) | (uint32_t) j;
-							pending = true;
-						}
-				}
-			}
-			if (__any_sync(0xFFFFFFFFu, pending)) {
-				__syncwarp();
-				const uint32_t c = *cnt;
-				if (c >= 32u || a == b) {
-					__syncwarp(); // every lane has read the count
-					if (lane == 0)
-						*cnt = 0;
-					for (uint32_t idx = lane; idx < c; idx += 32) {
-						const uint32_t p = list[idx];
-						best.take(exact_pair_sum<PACK16>(rows, (int) (p >> 16), (int) (p & 0xFFFFu)), p);
-					}
-					best.warp_min();
-					tq2 = (best.sum >> s) * 2u;
-					pending = false;
-					__syncwarp(); // list consumed and count reset before anyone appends again
-				}
-			}
+			for (int g = 0; g < 8; g += 4)
+				append(max(max(acc[g], acc[g + 1]), max(acc[g + 2], acc[g + 3])), thr, jok, i0 + g, j);
+			flush_if(a == b, a == b && (b == 0 || b == ntile - 1));
 		}
 	}
+#endif
 	__syncwarp();
 	return best.ij;
 }
@@ -460,7 +511,7 @@ struct RandLane {
 };
 
 template <int DXT, int CD>
-__global__ void __launch_bounds__(kSearchThreads, 32)
+__global__ void __launch_bounds__(kSearchThreads, S2TC_PS_MINCTAS)
 pair_search_kernel(ImageView v, int nrandom, int mcap, int sadj, uint32_t one, const uint32_t *__restrict__ windows, unsigned nchunks,
 		uint2 *__restrict__ ends)
 {
