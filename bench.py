@@ -163,7 +163,7 @@ def workload_config(args, wl, world):
     per_gpu = width * height * 4 // max(world, 1)
     return {"workload": f"{args.workload}: {dxt_n} {width}x{height} {gen}, S2TC_COLORDIST_MODE={cd_n}, "
                         f"S2TC_RANDOM_COLORS={nrandom}, S2TC_REFINE_COLORS={refine_n}, S2TC_DITHER_MODE={args.dither}",
-            "texture": f"{width}x{height} RGBA8", "sharding": f"contiguous block rows of the one texture, {world} shard(s)",
+            "texture": f"{width}x{height} RGBA8", "sharding": f"contiguous block rows of the one texture, {world} shard(s)" + (" (end to end: striped, see e2e.path)" if world > 1 else ""),
             "l2": (f"inputs {per_gpu >> 20} MiB per GPU exceed the 126 MiB L2; no flush needed"
                    if per_gpu > (126 << 20) else
                    f"inputs {per_gpu >> 20} MiB per GPU FIT the 126 MiB L2: a {max(per_gpu, 192 << 20) >> 20} MiB buffer is "
@@ -313,15 +313,29 @@ def run_texture(args, wl, world, rank, local, dist):
     mine = np.ascontiguousarray(img[y0:y1])
     h_src = torch.from_numpy(mine).pin_memory()
     h_dst = torch.empty(max(my_blocks * bs, 1), dtype=torch.uint8).pin_memory()
+    # N > 1, end to end: the texture is cut into NWAVE * world stripes of block rows, stripe w * world + rank belongs to this
+    # rank (s2tc_b200_compress_host_striped): wave w is encoded while wave w + 1 is uploaded.  Contiguous shards cannot
+    # overlap anything -- no shard can start before every shard above it has been uploaded and summarised.
+    WAVES = [1, 2, 4, 4, 3, 2]   # relative wave sizes: a small first wave starts the kernels early, a small last one ends the tail
+    NWAVE = len(WAVES)
+    stripes = [s2tc_b200.Encoder.stripe_rows(height, world, NWAVE, w, rank, WAVES) for w in range(NWAVE)] if world > 1 else []
+    if world > 1:
+        s_tex = [np.ascontiguousarray(img[4 * a:min(4 * b, height)]) for a, b in stripes]
+        hs_src = torch.from_numpy(np.concatenate([t.reshape(-1) for t in s_tex])).pin_memory()
+        hs_dst = torch.empty(max(sum((b - a) * bw * bs for a, b in stripes), 1), dtype=torch.uint8).pin_memory()
+        src_off = np.cumsum([0] + [t.size for t in s_tex])
+        dst_off = np.cumsum([0] + [(b - a) * bw * bs for a, b in stripes])
+        src_stripes = [hs_src[src_off[w]:src_off[w + 1]] if stripes[w][1] > stripes[w][0] else None for w in range(NWAVE)]
+        dst_stripes = [hs_dst[dst_off[w]:dst_off[w + 1]] if stripes[w][1] > stripes[w][0] else None for w in range(NWAVE)]
+        del s_tex
     d_src = h_src.cuda(non_blocking=False)
     d_dst = torch.empty(max(my_blocks * bs, 1), dtype=torch.uint8, device="cuda")
     # a non-default stream: its handle is what the C ABI launches on, and torch events recorded on it
     # bracket exactly those launches (the legacy default stream's handle is 0 = "use the context's own")
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    NSLAB = 8
-    maps_mine = torch.zeros(16 * NSLAB, dtype=torch.int64, device="cuda")
-    maps_all = torch.zeros(16 * NSLAB * world, dtype=torch.int64, device="cuda")
+    maps_mine = torch.zeros(16 * NWAVE, dtype=torch.int64, device="cuda")
+    maps_all = torch.zeros(16 * NWAVE * world, dtype=torch.int64, device="cuda")
     maps1_all = torch.zeros(16 * world, dtype=torch.int64, device="cuda")
     carry_dev = torch.zeros(4, dtype=torch.int32, device="cuda")
     per_gpu_bytes = (y1 - y0) * width * 4
@@ -340,9 +354,21 @@ def run_texture(args, wl, world, rank, local, dist):
     def step_e2e():
         if world == 1:
             enc.compress(h_src, st, cursor=0, out=h_dst)   # the reference-facing host call, pinned buffers
-        else:               # the same slab pipeline per shard; the carry exchange happens when every shard has been summarised
-            enc.compress_shard(h_src, width, height, row0, row1, h_dst, st, rank, NSLAB, maps_mine, maps_all,
-                               lambda: dist.all_gather_into_tensor(maps_all, maps_mine), cursor0=0, stream=stream.cuda_stream)
+        else:               # striped shards: one 128-byte all-gather per wave, uploads / kernels / downloads overlap
+            enc.compress_striped(src_stripes, width, height, dst_stripes, st, rank, world, NWAVE, maps_mine, maps_all,
+                                 lambda w: dist.all_gather_into_tensor(maps_all[16 * world * w:16 * world * (w + 1)],
+                                                                       maps_mine[16 * w:16 * (w + 1)]),
+                                 cursor0=0, stream=stream.cuda_stream, weights=WAVES)
+
+    def row_checksum(buf, rows):
+        """sum over block rows of (row number + 1) * crc32(row bytes): equal for two partitions of the same image"""
+        import zlib
+        tot, o = 0, 0
+        for a, b in rows:
+            for r in range(a, b):
+                tot += (r + 1) * zlib.crc32(buf[o:o + bw * bs].tobytes())
+                o += bw * bs
+        return tot % (1 << 62)
 
     def barrier():
         if dist is not None:
@@ -379,9 +405,17 @@ def run_texture(args, wl, world, rank, local, dist):
                 want = O.orc_rows(img, st.dxt, st.cd, st.nrandom, st.refine, st.dither, (a, b), cursor=0)
                 ok = ok and np.array_equal(got_dev[(a - row0) * bw * bs:(b - row0) * bw * bs], want)
                 checked += (b - a) * bw
-        step_e2e()     # and the host path of this rank must give the same bytes as its device path
+        step_e2e()     # and the host path must give the same bytes as the device path
         torch.cuda.synchronize()
-        ok = ok and np.array_equal(h_dst[:my_blocks * bs].numpy(), got_dev)
+        if world == 1:
+            ok = ok and np.array_equal(h_dst[:my_blocks * bs].numpy(), got_dev)
+        else:          # the ranks own different rows in the two paths: compare checksums over all block rows of the image
+            sums = torch.tensor([row_checksum(got_dev, [(row0, row1)]), row_checksum(hs_dst.numpy(), stripes)], dtype=torch.int64,
+                                device="cuda")
+            gathered = [torch.zeros_like(sums) for _ in range(world)]
+            dist.all_gather(gathered, sums)
+            tot = [sum(int(g[k].item()) for g in gathered) % (1 << 62) for k in (0, 1)]
+            ok = ok and tot[0] == tot[1]
         if not all_ok(ok):
             raise SystemExit("bench.py: GPU output differs from the oracle; refusing to report a number")
         if dist is not None:
@@ -583,8 +617,9 @@ def run_texture(args, wl, world, rank, local, dist):
         "e2e": {"value": e2e_value, "unit": "Mblocks/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": width * height * 4,
                 "d2h_bytes_per_step": total_blocks * bs,
                 "path": "s2tc_b200_compress_host (what tx_compress_dxtn calls), pinned host buffers" if world == 1
-                else "s2tc_b200_compress_host_shard per rank (slab-pipelined H2D / kernels / D2H, one all-gather of the "
-                     "DITHER_SIMPLE summaries), pinned host buffers",
+                else f"s2tc_b200_compress_host_striped per rank: {NWAVE} waves (sizes {WAVES}) x {world} stripes of block rows, stripe w * world + rank "
+                     "on rank `rank`; wave w is encoded while wave w + 1 is uploaded; one 128-byte all-gather of DITHER_SIMPLE "
+                     "summaries per wave (NCCL); pinned host buffers",
                 "copy_only": copy_only, "pageable": pageable},
         "gpu_launches": launches, "clocks": clocks,
         "checked_blocks_vs_oracle": checked,

@@ -119,12 +119,50 @@ int s2tc_b200_encode_rows_after_summary_async(s2tc_b200_ctx *ctx, const s2tc_b20
  * pipelined in nslab pieces.  DITHER_SIMPLE: d_maps_mine (nslab*128 bytes, device) receives this shard's summaries;
  * gather(user) is called once and must enqueue on `stream` an all-gather of every shard's d_maps_mine into d_maps_all
  * (world*nslab*128 bytes, device, rank order) -- ncclAllGather, torch.distributed.all_gather_into_tensor ...; nslab
- * (1..64) must be the same on every shard.  Other dither modes: gather is not called (FLOYDSTEINBERG cannot be sharded:
- * S2TC_B200_EUNSUPPORTED).  Returns when the shard's blocks are in dest.  (the whole-image form is
+ * (1..64) must be the same on every shard.  Other dither modes: gather is not called (FLOYDSTEINBERG shards are a chain:
+ * s2tc_b200_floyd_rows_device; here S2TC_B200_EUNSUPPORTED).  Returns when the shard's blocks are in dest.  (the whole-image form is
  * s2tc_b200_compress_host.) */
 int s2tc_b200_compress_host_shard(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int srccomps, int width, int height,
 		const uint8_t *src_rows, int row0, int row1, uint8_t *dest, uint64_t rand_cursor0, int rank, int nslab, void *d_maps_mine,
 		void *d_maps_all, void (*gather)(void *user), void *user, void *stream);
+
+/* ---- DITHER_FLOYDSTEINBERG for row shards (reference rgb565_image, s2tc_algorithm.cpp:1350-1412) ------------------------
+ * Error diffusion couples every texel row to the row above, so shards of one image run as a chain: a shard needs the
+ * error row its upper neighbour sent below its last row.  One call = one pass over the texel rows of block rows
+ * [row0, row1) (d_src_rows: texel row 4*row0; d_reduced_rows: the shard's reduced texels, 4 bytes each, both passes write
+ * their bytes into it):
+ *   phase 0 (r, g, b): d_err_in = [3][width] ints from the shard above (NULL for the image's first rows);
+ *                      d_err_out = [3][width] ints for the shard below -- or, from the image's LAST rows, the seed of the
+ *                      alpha pass in its first `width` ints (the reference's alpha pass starts from the red scratch row the
+ *                      colour pass left behind, :1380,1397);
+ *   phase 1 (alpha; srccomps 4 and alphabits 1 or 4 only): d_err_in = [width] ints: for the image's first rows the seed
+ *                      from the last rows' phase 0, otherwise the upper neighbour's d_err_out; d_err_out = [width] ints.
+ * Chain for N shards: phase 0 on shard 0, 1, ..., N-1 (each handing d_err_out to the next), then -- if there is an alpha
+ * pass -- the seed goes from shard N-1 to shard 0 and phase 1 runs down the shards the same way.  The result is then
+ * encoded with s2tc_b200_encode_reduced_rows_device.  A chain has no parallelism between shards (the recurrence has none):
+ * sharding Floyd-Steinberg distributes memory and the block encoder's work, not the pre-pass. */
+int s2tc_b200_floyd_rows_device(s2tc_b200_ctx *ctx, int srccomps, int alphabits, int width, int height, const void *d_src_rows,
+		int row0, int row1, int phase, const int *d_err_in, int *d_err_out, void *d_reduced_rows, void *stream);
+/* block rows [row0, row1) from texels the caller has already reduced (4 bytes each {r5, g6, b5, a}; s->dither is ignored) */
+int s2tc_b200_encode_reduced_rows_device(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int width, int height,
+		const void *d_reduced_rows, int row0, int row1, void *d_dst, uint64_t rand_cursor0, void *stream);
+
+/* ---- the same, STRIPED: several GPUs encode one texture and overlap their uploads with their kernels ----------------
+ * The block rows are cut into nwave waves -- in proportion to wave_weights[0..nwave) (NULL: equal; small first and last
+ * waves shorten the head and the tail of the pipeline) -- and every wave evenly into `world` stripes of consecutive block
+ * rows; stripe wave*world + rank belongs to shard `rank` (s2tc_b200_stripe_rows gives its block rows [row0, row1); empty
+ * when there are more stripes than block rows).
+ * src_stripes[w] / dest_stripes[w]: host memory of this shard's stripe of wave w (texel row 4*row0; tight block rows).
+ * DITHER_SIMPLE with world > 1: after wave w is summarised, gather(user, w) is called and must enqueue on `stream` an
+ * all-gather of 128 bytes at d_maps_mine + 128*w of every shard into d_maps_all + 128*world*w (rank order); both are
+ * device buffers (nwave*128 and nwave*world*128 bytes).  A contiguous shard (s2tc_b200_compress_host_shard) cannot encode
+ * anything before every shard above it has been uploaded; striped, wave w is encoded while wave w+1 is uploaded.
+ * Each stripe is a contiguous run of the reference's block-row loop (s2tc_libtxc_dxtn.cpp:246-258); carry and rand()
+ * cursor cross stripe boundaries exactly as they cross slab boundaries in the whole-image call. */
+void s2tc_b200_stripe_rows(int height, int world, int nwave, const int *wave_weights, int wave, int rank, int *row0, int *row1);
+int s2tc_b200_compress_host_striped(s2tc_b200_ctx *ctx, const s2tc_b200_settings *s, int srccomps, int width, int height,
+		const uint8_t *const *src_stripes, uint8_t *const *dest_stripes, uint64_t rand_cursor0, int rank, int world, int nwave,
+		const int *wave_weights, void *d_maps_mine, void *d_maps_all, void (*gather)(void *user, int wave), void *user, void *stream);
 
 /* ---- whole mip chain of an RGBA8 image on the device (SURVEY "next" N2) -----------------------------------
  * What the reference tool does per file after the DDS header (s2tc_compress.c:722-733): encode the level with

@@ -28,6 +28,7 @@ _DITHER_NAMES = ["NONE", "SIMPLE", "FLOYDSTEINBERG"]
 
 _u8p = C.POINTER(C.c_ubyte)
 GATHER_FN = C.CFUNCTYPE(None, C.c_void_p)   # the exchange callback of s2tc_b200_compress_host_shard
+GATHER_WAVE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int)   # ... of s2tc_b200_compress_host_striped (user, wave)
 
 
 class S2TCError(RuntimeError):
@@ -138,6 +139,12 @@ def lib():
     L.s2tc_b200_encode_rows_async.argtypes = [vp, sp, i32, i32, i32, vp, i32, i32, vp, u64, vp, vp]
     L.s2tc_b200_encode_rows_after_summary_async.argtypes = [vp, sp, i32, i32, i32, vp, i32, i32, vp, u64, vp, vp]
     L.s2tc_b200_compress_host_shard.argtypes = [vp, sp, i32, i32, i32, vp, i32, i32, vp, u64, i32, i32, vp, vp, GATHER_FN, vp, vp]
+    L.s2tc_b200_compress_host_striped.argtypes = [vp, sp, i32, i32, i32, C.POINTER(vp), C.POINTER(vp), u64, i32, i32, i32,
+                                                  C.POINTER(i32), vp, vp, GATHER_WAVE_FN, vp, vp]
+    L.s2tc_b200_floyd_rows_device.argtypes = [vp, i32, i32, i32, i32, vp, i32, i32, i32, vp, vp, vp, vp]
+    L.s2tc_b200_encode_reduced_rows_device.argtypes = [vp, sp, i32, i32, vp, i32, i32, vp, u64, vp]
+    L.s2tc_b200_stripe_rows.argtypes = [i32, i32, i32, C.POINTER(i32), i32, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.s2tc_b200_stripe_rows.restype = None
     L.s2tc_b200_carry_apply.argtypes = [C.POINTER(u64), i32, i32, i32, i32]
     L.s2tc_b200_mipchain_bytes.argtypes = [i32, i32, i32]
     L.s2tc_b200_mipchain_bytes.restype = C.c_size_t
@@ -328,6 +335,42 @@ class Encoder:
         _check(lib().s2tc_b200_compress_host_shard(self._ctx, C.byref(s), comps, width, height, _addr(src_rows), row0, row1,
                                                    _addr(dst), cursor0, rank, nslab, _addr(maps_mine), _addr(maps_all), cb, None,
                                                    stream))
+
+    def floyd_rows_device(self, src_rows, width, height, comps, alphabits, row0, row1, phase, err_in, err_out, reduced_rows,
+                          stream=None):
+        """One DITHER_FLOYDSTEINBERG pass (0: colour, 1: alpha) over the texel rows of block rows [row0, row1); err_in /
+        err_out: device int32 tensors ([3 * width] / [width]) or None (s2tc_b200_floyd_rows_device)."""
+        _check(lib().s2tc_b200_floyd_rows_device(self._ctx, comps, alphabits, width, height, _addr(src_rows), row0, row1, phase,
+                                                 None if err_in is None else _addr(err_in),
+                                                 None if err_out is None else _addr(err_out), _addr(reduced_rows), stream))
+
+    def encode_reduced_rows_device(self, reduced_rows, width, height, row0, row1, dst, settings, cursor0=0, stream=None):
+        s = settings.c()
+        _check(lib().s2tc_b200_encode_reduced_rows_device(self._ctx, C.byref(s), width, height, _addr(reduced_rows), row0, row1,
+                                                          _addr(dst), cursor0, stream))
+
+    @staticmethod
+    def stripe_rows(height, world, nwave, wave, rank, weights=None):
+        """Block rows [row0, row1) of stripe wave * world + rank (s2tc_b200_stripe_rows); weights: relative wave sizes."""
+        a, b = C.c_int(), C.c_int()
+        wts = (C.c_int * nwave)(*weights) if weights is not None else None
+        lib().s2tc_b200_stripe_rows(height, world, nwave, wts, wave, rank, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def compress_striped(self, src_stripes, width, height, dst_stripes, settings, rank, world, nwave, maps_mine=None,
+                         maps_all=None, all_gather=None, comps=4, cursor0=0, stream=None, weights=None):
+        """Host to host, one texture on `world` shards in nwave * world stripes (s2tc_b200_compress_host_striped).
+        src_stripes[w] / dst_stripes[w]: this shard's stripe of wave w (numpy arrays or pinned torch tensors; None for an
+        empty stripe).  all_gather(w): gathers maps_mine[16 w : 16 w + 16] (int64, device) of every rank into
+        maps_all[16 world w : 16 world (w + 1)] on `stream` (DITHER_SIMPLE, world > 1)."""
+        s = settings.c()
+        srcs = (C.c_void_p * nwave)(*[None if a is None else _addr(a) for a in src_stripes])
+        dsts = (C.c_void_p * nwave)(*[None if a is None else _addr(a) for a in dst_stripes])
+        cb = GATHER_WAVE_FN((lambda _user, w: all_gather(w)) if all_gather else (lambda _user, w: None))
+        wts = (C.c_int * nwave)(*weights) if weights is not None else None
+        _check(lib().s2tc_b200_compress_host_striped(self._ctx, C.byref(s), comps, width, height, srcs, dsts, cursor0, rank, world,
+                                                     nwave, wts, None if maps_mine is None else _addr(maps_mine),
+                                                     None if maps_all is None else _addr(maps_all), cb, None, stream))
 
     def dither_summary_device(self, src_rows, width, height, comps, alphabits, row0, row1, stream=None):
         maps = (C.c_uint64 * 16)()

@@ -234,7 +234,7 @@ int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &
 // ready_ws: a dither workspace that already holds the chunk/tile maps of exactly these texels (phase 1 is skipped), or NULL.
 int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int width, int height,
 		const void *d_src_rows, int row0, int row1, void *d_dst, uint64_t cursor0, int *d_carry, cudaStream_t st,
-		void *ready_ws = nullptr)
+		void *ready_ws = nullptr, bool src_is_reduced = false)
 {
 	const int bh = (height + 3) / 4, bw = (width + 3) / 4;
 	if (width <= 0 || height <= 0 || row0 < 0 || row1 > bh || row0 > row1)
@@ -250,7 +250,10 @@ int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int
 	const uint8_t *texels = (const uint8_t *) d_src_rows;
 	int fmt = comps == 3 ? kSrcRGB8 : kSrcRGBA8;
 	size_t texel_bytes = comps;
-	if (s.dither == kDitherSimple) {
+	if (src_is_reduced) { // the caller ran the 565 pre-pass itself (s2tc_b200_floyd_rows_device): 4 bytes per texel {r5, g6, b5, a}
+		fmt = kSrcReduced;
+		texel_bytes = 4;
+	} else if (s.dither == kDitherSimple) {
 		CU(c->reduced.reserve(npix * 4));
 		CU(c->dither_ws.reserve(dither_workspace_bytes(npix)));
 		int *carry = d_carry;
@@ -602,6 +605,30 @@ int compress_rows_host(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int comps,
 		nslab = nrows;
 	if (row_bytes < tight || s.dither == kDitherFloyd)
 		nslab = 1; // overlapping destination rows: single ordered copy at the end; Floyd-Steinberg: one 2-D recurrence
+	// Random candidates: every launch of the search kernel ends with a tail in which the last chunks (one warp, ~0.3 ms
+	// each) run on a mostly idle GPU -- measured 0.26 ms per slab whatever its size (tools_lab/e2e_c3.py: 8 / 16 / 32 / 64
+	// slabs).  So the slabs GROW: the first one is small (the kernels start after 16 MiB are up, not 64), every next one
+	// twice as large up to 256 MiB; the upload (~52 GB/s) stays ahead of the kernels (~25 GB/s of texels) from the second
+	// slab on.  first_rows > 0 selects this schedule.
+	int first_rows = 0, cap_rows = 0;
+	if (s.nrandom > 0 && !exchange && nslab > 1 && !getenv("S2TC_B200_SLAB_MB")) {
+		const size_t row_in = (size_t) width * 4 * comps; // texel bytes per block row
+		first_rows = (int) (((size_t) 16 << 20) / row_in);
+		cap_rows = (int) (((size_t) 256 << 20) / row_in);
+		if (first_rows < 1 || cap_rows < first_rows) {
+			first_rows = 0;
+		} else {
+			int n = 0, left = nrows, sz = first_rows;
+			while (left > 0) {
+				left -= sz;
+				if (left > 0 && left * 2 < sz) // a small remainder joins the last slab instead of costing a launch of its own
+					left = 0;
+				sz = sz * 2 < cap_rows ? sz * 2 : cap_rows;
+				++n;
+			}
+			nslab = n;
+		}
+	}
 	int *d_carry = nullptr;
 	if (s.dither == kDitherSimple) {
 		d_carry = (int *) c->small.p + 8;
@@ -616,6 +643,17 @@ int compress_rows_host(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int comps,
 	cudaEvent_t t0 = nullptr;
 	const bool pipelined = nslab > 1 || exchange;
 	auto slab_rows = [&](int i, int &r0, int &r1) {
+		if (first_rows > 0) { // growing slabs
+			long long a = 0, sz = first_rows;
+			for (int k = 0; k < i; ++k) {
+				a += sz;
+				sz = sz * 2 < cap_rows ? sz * 2 : cap_rows;
+			}
+			const long long b = i == nslab - 1 ? nrows : a + sz;
+			r0 = row0 + (int) (a < nrows ? a : nrows);
+			r1 = row0 + (int) (b < nrows ? b : nrows);
+			return;
+		}
 		r0 = row0 + (int) ((long long) nrows * i / nslab);
 		r1 = row0 + (int) ((long long) nrows * (i + 1) / nslab);
 	};
@@ -805,6 +843,199 @@ int s2tc_b200_compress_host_shard(s2tc_b200_ctx *c, const s2tc_b200_settings *si
 	CarryExchange ex{rank, nslab, (ByteMap *) d_maps_mine, (ByteMap *) d_maps_all, gather, user};
 	const size_t tight = (size_t) ((width + 3) / 4) * block_bytes(s.dxt);
 	return compress_rows_host(c, s, comps, width, height, src_rows, row0, row1, dest, tight, rand_cursor0, exchange ? &ex : nullptr, st);
+}
+
+// DITHER_FLOYDSTEINBERG for row shards: see include/s2tc_b200.h
+int s2tc_b200_floyd_rows_device(s2tc_b200_ctx *c, int srccomps, int alphabits, int width, int height, const void *d_src_rows, int row0,
+		int row1, int phase, const int *d_err_in, int *d_err_out, void *d_reduced_rows, void *stream)
+{
+	if (!c || !d_src_rows || !d_reduced_rows)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	const int bh = (height + 3) / 4;
+	if (width <= 0 || height <= 0 || row0 < 0 || row1 > bh || row0 >= row1 || (phase != 0 && phase != 1))
+		return fail(S2TC_B200_EINVAL, "bad geometry %dx%d rows [%d,%d) phase %d", width, height, row0, row1, phase);
+	const int comps = srccomps == 3 ? 3 : 4;
+	if (phase == 1 && (comps != 4 || (alphabits != 1 && alphabits != 4)))
+		return fail(S2TC_B200_EINVAL, "the alpha pass exists for 4-component sources and 1- or 4-bit alpha only (ref s2tc_algorithm.cpp:1374-1404)");
+	if (alphabits != 1 && alphabits != 4 && alphabits != 8)
+		return fail(S2TC_B200_EINVAL, "alphabits %d", alphabits);
+	const int y0 = row0 * 4, y1 = row1 * 4 < height ? row1 * 4 : height;
+	if (row1 < bh && !d_err_out)
+		return fail(S2TC_B200_EINVAL, "rows [%d,%d) of %d have rows below them: d_err_out is needed", row0, row1, bh);
+	if (phase == 1 && !d_err_in)
+		return fail(S2TC_B200_EINVAL, "the alpha pass needs d_err_in (first rows: the seed the last rows' colour pass left)");
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	StreamOrder order(c, st);
+	CU(c->dither_ws.reserve(floyd_workspace_bytes(width, y1 - y0)));
+	FamScope f(c, st, kFamPrepass, row1 < bh ? 2 : 1);
+	CU(launch_floyd_rows(d_src_rows, comps, alphabits, width, height, y0, y1 - y0, phase, d_err_in, d_err_out, d_reduced_rows,
+			c->dither_ws.p, st));
+	return 0;
+}
+
+// Block rows [row0, row1) of an image whose 565 pre-pass the caller has already run: d_reduced_rows = reduced texels
+// {r5, g6, b5, a}, 4 bytes each, of texel row 4 * row0 onwards.  s->dither is ignored.
+int s2tc_b200_encode_reduced_rows_device(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int width, int height,
+		const void *d_reduced_rows, int row0, int row1, void *d_dst, uint64_t rand_cursor0, void *stream)
+{
+	if (!c || !d_reduced_rows || !d_dst)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	s2tc_b200_settings s;
+	if (int rc = settings_normalise(sin, s))
+		return rc;
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	StreamOrder order(c, st);
+	return encode_rows(c, s, 4, width, height, d_reduced_rows, row0, row1, d_dst, rand_cursor0, nullptr, st, nullptr, true);
+}
+
+void s2tc_b200_stripe_rows(int height, int world, int nwave, const int *wave_weights, int wave, int rank, int *row0, int *row1)
+{
+	// wave w covers block rows [bh * cum(w) / total, bh * cum(w + 1) / total) and is cut evenly among the shards
+	const long long bh = (height + 3) / 4;
+	long long total = 0, before = 0, mine = 1;
+	for (int w = 0; w < nwave; ++w) {
+		const long long x = wave_weights ? (wave_weights[w] > 0 ? wave_weights[w] : 0) : 1;
+		if (w < wave)
+			before += x;
+		if (w == wave)
+			mine = x;
+		total += x;
+	}
+	if (total <= 0 || wave < 0 || wave >= nwave) {
+		*row0 = *row1 = 0;
+		return;
+	}
+	const long long a = bh * before / total, b = bh * (before + mine) / total;
+	*row0 = (int) (a + (b - a) * rank / world);
+	*row1 = (int) (a + (b - a) * (rank + 1) / world);
+}
+
+// One texture, `world` shards, STRIPED: the block rows are cut into nwave * world stripes of consecutive block rows and
+// stripe wave * world + rank belongs to shard `rank` (s2tc_b200_stripe_rows).  Why not one contiguous range per shard
+// (s2tc_b200_compress_host_shard): with DITHER_SIMPLE a shard cannot start before every shard above it is uploaded and
+// summarised, and all shards upload at the same pace -- nothing is encoded until everything is on the devices.  Striped,
+// wave w of every shard lands at about the same time, its summaries are exchanged (128 bytes per shard and wave) and the
+// stripes are encoded while wave w + 1 is on its way: uploads, kernels and downloads overlap on every GPU.
+int s2tc_b200_compress_host_striped(s2tc_b200_ctx *c, const s2tc_b200_settings *sin, int srccomps, int width, int height,
+		const uint8_t *const *src_stripes, uint8_t *const *dest_stripes, uint64_t rand_cursor0, int rank, int world, int nwave,
+		const int *wave_weights, void *d_maps_mine, void *d_maps_all, void (*gather)(void *, int), void *user, void *stream)
+{
+	if (!c || !src_stripes || !dest_stripes)
+		return fail(S2TC_B200_EINVAL, "NULL argument");
+	s2tc_b200_settings s;
+	if (int rc = settings_normalise(sin, s))
+		return rc;
+	if (width <= 0 || height <= 0 || world < 1 || rank < 0 || rank >= world || nwave < 1 || nwave > 256)
+		return fail(S2TC_B200_EINVAL, "bad geometry %dx%d rank %d of %d, %d waves", width, height, rank, world, nwave);
+	if (s.dither == kDitherFloyd)
+		return fail(S2TC_B200_EUNSUPPORTED, "DITHER_FLOYDSTEINBERG diffuses error between rows: use s2tc_b200_floyd_rows_device per shard");
+	const bool simple = s.dither == kDitherSimple;
+	const bool exchange = simple && world > 1;
+	if (exchange && (!gather || !d_maps_mine || !d_maps_all))
+		return fail(S2TC_B200_EINVAL, "DITHER_SIMPLE stripes of several shards need gather, d_maps_mine and d_maps_all");
+	std::lock_guard<std::mutex> lock(c->mu);
+	CU(cudaSetDevice(c->device));
+	cudaStream_t st = stream ? (cudaStream_t) stream : c->stream;
+	StreamOrder order(c, st);
+	const int comps = srccomps == 3 ? 3 : 4, abits = alpha_bits(s.dxt);
+	const size_t tight = (size_t) ((width + 3) / 4) * block_bytes(s.dxt);
+
+	struct Stripe {
+		int r0, r1;
+		size_t in_off, in_len, out_off, out_len, ws_off;
+	};
+	std::vector<Stripe> sp(nwave);
+	size_t in_total = 0, out_total = 0, ws_total = 0;
+	for (int w = 0; w < nwave; ++w) {
+		Stripe &q = sp[w];
+		s2tc_b200_stripe_rows(height, world, nwave, wave_weights, w, rank, &q.r0, &q.r1);
+		const int y0 = q.r0 * 4, y1 = q.r1 * 4 < height ? q.r1 * 4 : height;
+		q.in_off = in_total;
+		q.in_len = (size_t) width * (y1 - y0) * comps;
+		q.out_off = out_total;
+		q.out_len = tight * (q.r1 - q.r0);
+		q.ws_off = ws_total;
+		in_total += (q.in_len + 255) & ~(size_t) 255;
+		out_total += (q.out_len + 255) & ~(size_t) 255;
+		if (simple && q.in_len)
+			ws_total += (dither_workspace_bytes(q.in_len / comps) + 255) & ~(size_t) 255;
+		if (q.in_len && (!src_stripes[w] || !dest_stripes[w]))
+			return fail(S2TC_B200_EINVAL, "stripe %d has no source or destination", w);
+	}
+	CU(c->src.reserve(in_total ? in_total : 1));
+	CU(c->out.reserve(out_total ? out_total : 1));
+	if (ws_total)
+		CU(c->shard_ws.reserve(ws_total));
+	int *d_carry = simple ? (int *) c->small.p + 8 : nullptr;  // carry entering the current stripe
+	int *d_wave = (int *) c->small.p + 24;                     // carry entering the current wave's first stripe
+	ByteMap *d_mine = (ByteMap *) d_maps_mine, *d_all = (ByteMap *) d_maps_all;
+	std::vector<cudaEvent_t> up(nwave, nullptr), done(nwave, nullptr);
+	cudaEvent_t t0 = nullptr;
+	const int rc = [&]() -> int {
+		for (int w = 0; w < nwave; ++w) {
+			CU(cudaEventCreateWithFlags(&up[w], cudaEventDisableTiming));
+			CU(cudaEventCreateWithFlags(&done[w], cudaEventDisableTiming));
+		}
+		CU(cudaEventCreateWithFlags(&t0, cudaEventDisableTiming));
+		CU(cudaEventRecord(t0, st));
+		CU(cudaStreamWaitEvent(c->copy_in, t0, 0));
+		CU(cudaStreamWaitEvent(c->copy_out, t0, 0));
+		if (simple)
+			CU(cudaMemsetAsync(exchange ? d_wave : d_carry, 0, 4 * sizeof(int), st));
+		for (int w = 0; w < nwave; ++w) { // all uploads are queued at once; the compute stream takes them as they land
+			if (sp[w].in_len)
+				CU(cudaMemcpyAsync((uint8_t *) c->src.p + sp[w].in_off, src_stripes[w], sp[w].in_len, cudaMemcpyHostToDevice, c->copy_in));
+			CU(cudaEventRecord(up[w], c->copy_in));
+		}
+		for (int w = 0; w < nwave; ++w) {
+			const Stripe &q = sp[w];
+			const uint8_t *d_in = (const uint8_t *) c->src.p + q.in_off;
+			uint8_t *ws = ws_total ? (uint8_t *) c->shard_ws.p + q.ws_off : nullptr;
+			CU(cudaStreamWaitEvent(st, up[w], 0));
+			if (exchange) {
+				{
+					FamScope f(c, st, kFamPrepass, q.in_len ? kDitherSummaryLaunches : 1);
+					if (q.in_len)
+						CU(launch_dither_summary(d_in, comps, abits, q.in_len / comps, d_mine + 4 * w, ws, st));
+					else
+						CU(launch_identity_maps(d_mine + 4 * w, 1, comps, abits, st));
+				}
+				gather(user, w); // d_mine[w] of every shard -> d_all[w * world ..], on st
+				FamScope f(c, st, kFamPrepass, 2);
+				const ByteMap *wave_maps = d_all + (size_t) 4 * world * w;
+				CU(launch_fold_carry_from(wave_maps, rank, comps, abits, d_wave, d_carry, st));
+				CU(launch_fold_carry_from(wave_maps, world, comps, abits, d_wave, d_wave, st));
+			}
+			if (q.r1 > q.r0) {
+				uint8_t *d_out = (uint8_t *) c->out.p + q.out_off;
+				if (int e = encode_rows(c, s, comps, width, height, d_in, q.r0, q.r1, d_out, rand_cursor0, d_carry, st, exchange ? ws : nullptr))
+					return e;
+				CU(cudaEventRecord(done[w], st));
+				CU(cudaStreamWaitEvent(c->copy_out, done[w], 0));
+				CU(cudaMemcpyAsync(dest_stripes[w], d_out, q.out_len, cudaMemcpyDeviceToHost, c->copy_out));
+			}
+		}
+		return 0;
+	}();
+	const cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(c->copy_in), e3 = cudaStreamSynchronize(c->copy_out);
+	for (int w = 0; w < nwave; ++w) {
+		if (up[w])
+			cudaEventDestroy(up[w]);
+		if (done[w])
+			cudaEventDestroy(done[w]);
+	}
+	if (t0)
+		cudaEventDestroy(t0);
+	if (rc)
+		return rc;
+	CU(e1);
+	CU(e2);
+	CU(e3);
+	return 0;
 }
 
 size_t s2tc_b200_mipchain_bytes(int dxt, int width, int height)

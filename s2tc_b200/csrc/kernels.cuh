@@ -209,11 +209,18 @@ cudaError_t launch_dither_summary(const void *d_src, int srccomps, int alphabits
 // carry entering a range = the first `rank` summaries of d_maps (4 ByteMaps each) applied in order to a zero carry
 cudaError_t launch_fold_carry(const ByteMap *d_maps, int rank, int srccomps, int alphabits, int *d_carry, cudaStream_t stream);
 cudaError_t launch_identity_maps(ByteMap *d_maps, int count, int srccomps, int alphabits, cudaStream_t stream);
+// the same fold over `count` summaries starting from the carry in d_carry_in (device; NULL = zero; may alias d_carry)
+cudaError_t launch_fold_carry_from(const ByteMap *d_maps, int count, int srccomps, int alphabits, const int *d_carry_in, int *d_carry,
+		cudaStream_t stream);
 
 // DITHER_FLOYDSTEINBERG over a whole width x height image (a 2-D recurrence: it cannot start in the middle)
 size_t floyd_workspace_bytes(int width, int height);
 cudaError_t launch_prepass_floyd(const void *d_src, int srccomps, int alphabits, int width, int height, void *d_reduced,
 		void *d_workspace, cudaStream_t stream);
+// one pass (phase 0: r, g, b; phase 1: alpha) over `rows` texel rows starting at row y0 of an image of image_height rows; the error
+// rows that cross the cuts travel through d_err_in / d_err_out (kernels_floyd.cu).  Workspace: floyd_workspace_bytes(width, rows).
+cudaError_t launch_floyd_rows(const void *d_src_rows, int srccomps, int alphabits, int width, int image_height, int y0, int rows,
+		int phase, const int *d_err_in, int *d_err_out, void *d_reduced_rows, void *d_workspace, cudaStream_t stream);
 
 // one mip step of `images` RGBA8 images stored back to back (w x h -> max(w/2,1) x max(h/2,1) each, results back to back);
 // d_out must not alias d_in

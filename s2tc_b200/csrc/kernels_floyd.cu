@@ -39,7 +39,13 @@ struct FloydArgs {
 	int width, height, srccomps, alphabits;
 	uint2 *boundary;   // [bands][channels][width] {x + 1, error sent below the band's last row to texel x}; zeroed per pass
 	int *ticket;       // band dispenser, zeroed per pass
-	int *alpha_seed;   // [width] red-channel leftovers for the alpha pass (written by the colour pass)
+	int *alpha_seed;   // [width] red-channel leftovers for the alpha pass (written by the colour pass of the image's last rows)
+	// row shards (launch_floyd_rows): `height` rows of an image whose other rows are handled by other calls / GPUs
+	const int *seed;   // [channels][width] errors entering row 0 from the rows above (NULL: none); the alpha pass of an image's
+	                   // first rows is seeded with the red leftovers of its last row (ref :1380,1397)
+	bool more_below;   // the image continues below these rows: the last row publishes its errors like any band boundary
+	bool image_last;   // these rows end the image: their last row leaves the alpha seed
+	bool image_odd;    // parity of the IMAGE's height
 };
 
 // Boundary entries are single 64-bit words read and written with L2-level (.cg) accesses: a reader sees an entry whole or
@@ -69,6 +75,7 @@ struct FloydLane {
 	uint8_t *orow;
 	const uint2 *bin;
 	uint2 *bout;
+	const int *seedrow; // band 0: errors entering its first row, or NULL
 	uint32_t const_alpha;
 	int shift8;
 	int e7 = 0, p5 = 0, a1 = 0, b1 = 0, dout = 0;
@@ -122,8 +129,8 @@ struct FloydLane {
 					cur = nxt;
 					if (lane < 8 && (STEADY || HEAD || s + 8 + lane < w))
 						nxt = ld_entry(bin + s + 8 + lane);
-				} else if (ALPHA && band == 0) {
-					cur.y = (lane < 8 && s + lane < w) ? (uint32_t) a.alpha_seed[s + lane] : 0u; // the colour pass's leftovers seed alpha row 0
+				} else if (seedrow) { // band 0 of a seeded pass: the rows above (another shard), or the colour pass's leftovers (alpha)
+					cur.y = (lane < 8 && s + lane < w) ? (uint32_t) seedrow[s + lane] : 0u;
 				}
 			}
 			// error from the row above for texel x: computed by the lane above in the previous step
@@ -167,12 +174,13 @@ __device__ __forceinline__ void floyd_band(const FloydArgs &a, int band, int lan
 	const int row = band * 32 + lane;
 	const int w = a.width;
 	const int last_lane = min(31, a.height - 1 - band * 32); // lane of the band's last row
-	const bool image_last = row == a.height - 1;
+	const bool image_last = row == a.height - 1 && a.image_last;
 	Lane L{a, band, lane, ch, w};
 	L.live = row < a.height;
-	L.exports = lane == last_lane && row + 1 < a.height;
+	L.exports = lane == last_lane && (row + 1 < a.height || a.more_below);
 	L.seeds = !ALPHA && ch == 0 && image_last; // the red warp leaves the alpha pass its seed row
-	L.odd_height = a.height & 1;
+	L.odd_height = a.image_odd;
+	L.seedrow = (band == 0 && a.seed) ? a.seed + (size_t) chi * w : nullptr;
 	L.fill_alpha = !ALPHA && ch == 0 && (a.srccomps != 4 || a.alphabits == 8); // no alpha pass: copy or all ones
 	L.imports = band > 0; // warp-uniform
 	L.srow = a.src + (size_t) row * w * a.srccomps;
@@ -274,6 +282,10 @@ cudaError_t launch_prepass_floyd(const void *d_src, int srccomps, int alphabits,
 	a.ticket = (int *) d_workspace;                       // 256 bytes reserved
 	a.alpha_seed = a.ticket + 64;
 	a.boundary = (uint2 *) (((uintptr_t) (a.alpha_seed + width) + 255) & ~(uintptr_t) 255);
+	a.seed = nullptr;
+	a.more_below = false;
+	a.image_last = true;
+	a.image_odd = height & 1;
 	const size_t bbytes = (size_t) bands * width * 3 * sizeof(uint2);
 	cudaError_t e = cudaMemsetAsync(a.ticket, 0, 256, stream);
 	if (e == cudaSuccess)
@@ -286,10 +298,66 @@ cudaError_t launch_prepass_floyd(const void *d_src, int srccomps, int alphabits,
 			return e;
 		if ((e = cudaMemsetAsync(a.boundary, 0, (size_t) bands * width * sizeof(uint2), stream)) != cudaSuccess)
 			return e;
+		a.seed = a.alpha_seed;
 		if (alphabits == 1)
 			floyd_kernel<true, 7><<<bands, 32, 0, stream>>>(a);
 		else
 			floyd_kernel<true, 4><<<bands, 32, 0, stream>>>(a);
+	}
+	return cudaGetLastError();
+}
+
+// ---- row shards ---------------------------------------------------------------------------------------------------
+// The error row that crosses a shard boundary is the same thing as the row that crosses a band boundary; a shard's last
+// band publishes it in the boundary format and this kernel hands the caller plain ints.
+__global__ void boundary_errors_kernel(const uint2 *__restrict__ b, int n, int *__restrict__ out)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n)
+		out[i] = (int) b[i].y;
+}
+
+// One pass over `rows` texel rows starting at row y0 of an image of image_height rows.  phase 0: r, g, b (d_err_in /
+// d_err_out: [3][width] ints), phase 1: alpha (srccomps 4, alphabits 1 or 4 only; [width] ints).  d_err_in: the errors the
+// rows above sent down (NULL for the image's first rows in phase 0; in phase 1 the image's first rows take the seed the
+// LAST rows' phase 0 left in their d_err_out).  d_err_out: what these rows send below -- or, for phase 0 of the image's
+// last rows, the alpha seed in its first `width` ints.
+cudaError_t launch_floyd_rows(const void *d_src_rows, int srccomps, int alphabits, int width, int image_height, int y0, int rows,
+		int phase, const int *d_err_in, int *d_err_out, void *d_reduced_rows, void *d_workspace, cudaStream_t stream)
+{
+	if (width <= 0 || rows <= 0)
+		return cudaSuccess;
+	const int bands = (rows + 31) / 32;
+	const int nch = phase == 0 ? 3 : 1;
+	FloydArgs a;
+	a.src = (const uint8_t *) d_src_rows;
+	a.out = (uint32_t *) d_reduced_rows;
+	a.width = width;
+	a.height = rows;
+	a.srccomps = srccomps;
+	a.alphabits = alphabits;
+	a.ticket = (int *) d_workspace;
+	int *scratch_seed = a.ticket + 64;
+	a.boundary = (uint2 *) (((uintptr_t) (scratch_seed + width) + 255) & ~(uintptr_t) 255);
+	a.seed = d_err_in;
+	a.image_last = y0 + rows >= image_height;
+	a.more_below = !a.image_last;
+	a.image_odd = image_height & 1;
+	a.alpha_seed = (phase == 0 && a.image_last && d_err_out) ? d_err_out : scratch_seed;
+	cudaError_t e = cudaMemsetAsync(a.ticket, 0, 256, stream);
+	if (e == cudaSuccess)
+		e = cudaMemsetAsync(a.boundary, 0, (size_t) bands * width * nch * sizeof(uint2), stream);
+	if (e != cudaSuccess)
+		return e;
+	if (phase == 0)
+		floyd_kernel<false, 3><<<bands, 96, 0, stream>>>(a);
+	else if (alphabits == 1)
+		floyd_kernel<true, 7><<<bands, 32, 0, stream>>>(a);
+	else
+		floyd_kernel<true, 4><<<bands, 32, 0, stream>>>(a);
+	if (a.more_below && d_err_out) {
+		const int n = nch * width;
+		boundary_errors_kernel<<<(n + 255) / 256, 256, 0, stream>>>(a.boundary + (size_t) (bands - 1) * nch * width, n, d_err_out);
 	}
 	return cudaGetLastError();
 }

@@ -703,12 +703,13 @@ static cudaError_t run_dither(int phases, const void *d_src, int srccomps, int a
 }
 
 // carry entering shard `rank` = summaries of shards 0 .. rank-1 applied in order to a zero carry (one thread per channel)
-__global__ void fold_carry_kernel(const ByteMap *__restrict__ maps, int rank, ChanKinds kinds, int *carry)
+// carry_in: the carry the chain starts from (NULL = zero; may be the same address as carry)
+__global__ void fold_carry_kernel(const ByteMap *__restrict__ maps, int rank, ChanKinds kinds, const int *carry_in, int *carry)
 {
 	const int ch = threadIdx.x;
 	if (ch >= 4)
 		return;
-	int c = 0;
+	int c = carry_in ? carry_in[ch] : 0;
 	for (int r = 0; r < rank; ++r)
 		c = bmap_apply(maps[r * 4 + ch], kinds.k[ch], c);
 	carry[ch] = c;
@@ -716,7 +717,14 @@ __global__ void fold_carry_kernel(const ByteMap *__restrict__ maps, int rank, Ch
 
 cudaError_t launch_fold_carry(const ByteMap *d_maps, int rank, int srccomps, int alphabits, int *d_carry, cudaStream_t stream)
 {
-	fold_carry_kernel<<<1, 32, 0, stream>>>(d_maps, rank, chan_kinds(srccomps, alphabits), d_carry);
+	fold_carry_kernel<<<1, 32, 0, stream>>>(d_maps, rank, chan_kinds(srccomps, alphabits), nullptr, d_carry);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_fold_carry_from(const ByteMap *d_maps, int count, int srccomps, int alphabits, const int *d_carry_in, int *d_carry,
+		cudaStream_t stream)
+{
+	fold_carry_kernel<<<1, 32, 0, stream>>>(d_maps, count, chan_kinds(srccomps, alphabits), d_carry_in, d_carry);
 	return cudaGetLastError();
 }
 

@@ -31,3 +31,38 @@ def summary_to_i64(words):
 
 def summary_from_i64(vals):
     return [int(v) & ((1 << 64) - 1) for v in vals]
+
+
+def floyd_steinberg_sharded(enc, dist, src_rows, width, height, comps, alphabits, row0, row1, rank, world, reduced_rows,
+                            new_ints, stream=None):
+    """DITHER_FLOYDSTEINBERG pre-pass of one image whose block rows [row0, row1) live on this rank (contiguous, non-empty
+    shards in rank order).  Error diffusion is a recurrence over rows, so the shards run as a chain
+    (s2tc_b200_floyd_rows_device): the colour pass goes down the ranks, each handing the error row below its last texel
+    row to the next rank; the reference's alpha pass is seeded with the red leftovers of the image's LAST row
+    (s2tc_algorithm.cpp:1380,1397), so the seed travels from the last rank to rank 0 and the alpha pass goes down the same
+    way.  dist: torch.distributed (send / recv on the current stream) or anything with the same two calls;
+    new_ints(n): a zeroed int32 buffer of n elements on the device the exchange uses.  Writes reduced_rows (4 bytes per
+    texel), to be encoded with Encoder.encode_reduced_rows_device."""
+    if row1 <= row0:
+        raise ValueError("Floyd-Steinberg shards must not be empty")
+    err_in, err_out = new_ints(3 * width), new_ints(3 * width)
+    if rank > 0:
+        dist.recv(err_in, src=rank - 1)
+    enc.floyd_rows_device(src_rows, width, height, comps, alphabits, row0, row1, 0, err_in if rank > 0 else None, err_out,
+                          reduced_rows, stream=stream)
+    if rank < world - 1:
+        dist.send(err_out, dst=rank + 1)
+    if comps != 4 or alphabits == 8:
+        return
+    seed, a_out = new_ints(width), new_ints(width)
+    if world == 1:
+        seed = err_out[:width]
+    elif rank == world - 1:
+        dist.send(err_out[:width].contiguous(), dst=0)
+    if rank == 0 and world > 1:
+        dist.recv(seed, src=world - 1)
+    if rank > 0:
+        dist.recv(seed, src=rank - 1)
+    enc.floyd_rows_device(src_rows, width, height, comps, alphabits, row0, row1, 1, seed, a_out, reduced_rows, stream=stream)
+    if rank < world - 1:
+        dist.send(a_out, dst=rank + 1)

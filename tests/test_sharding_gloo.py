@@ -64,6 +64,66 @@ def _worker(rank, world, port, ret):
     dist.all_gather(bufs, out) if len(set(sizes)) == 1 else None
     if len(set(sizes)) == 1:
         assert np.array_equal(torch.cat(bufs).numpy(), full)
+    # 4. striped shards (s2tc_b200_compress_host_striped): nwave * world stripes, stripe w * world + rank on this rank; per
+    #    wave one all-gather of the stripes' summaries, the carry entering a stripe = carry entering the wave folded over
+    #    the stripes of the ranks before us, the carry entering the next wave = folded over all of them
+    import s2tc_b200
+    nwave = 3
+    for dxt, abits in ((O.DXT1, 1), (O.DXT5, 8)):
+        want = O.orc_prepass(img, abits, O.DITHER_SIMPLE)
+        wave_carry = [0, 0, 0, 0]
+        for w in range(nwave):
+            a, b = s2tc_b200.Encoder.stripe_rows(height, world, nwave, w, rank)
+            wa, wb = bh * w // nwave, bh * (w + 1) // nwave      # the wave's rows, cut evenly among the ranks
+            assert (a, b) == (wa + (wb - wa) * rank // world, wa + (wb - wa) * (rank + 1) // world)
+            stripe = img[4 * a:4 * b]
+            summary = torch.tensor(summary_to_i64(H.dither_summary(stripe, 4, abits)), dtype=torch.int64)
+            gathered = [torch.empty_like(summary) for _ in range(world)]
+            dist.all_gather(gathered, summary)
+            sums = [summary_from_i64(g.tolist()) for g in gathered]
+            carry = fold_carry(sums, rank, 4, abits, wave_carry)
+            wave_carry = fold_carry(sums, world, 4, abits, wave_carry)
+            reduced, _ = H.prepass_range(stripe, 4, abits, carry)
+            assert np.array_equal(reduced.reshape(want[4 * a:4 * b].shape), want[4 * a:4 * b]), ("stripe", rank, w, dxt)
+
+    # 5. the Floyd-Steinberg chain (sharding.floyd_steinberg_sharded) over real point-to-point messages: a stand-in encoder
+    #    whose "passes" are a recurrence over rows with the same data flow (error row in, error row out, the alpha seed
+    #    leaving the image's last rows through the first `width` ints of the colour pass's output)
+    from s2tc_b200.sharding import floyd_steinberg_sharded
+
+    class FakeEnc:
+        def floyd_rows_device(self, src_rows, width, height, comps, alphabits, row0, row1, phase, err_in, err_out, reduced, stream=None):
+            n = 3 * width if phase == 0 else width
+            e = torch.zeros(n, dtype=torch.int32) if err_in is None else err_in.clone()
+            for y in range(src_rows.shape[0]):
+                e = (e * 3 + int(src_rows[y].sum()) + phase) % 1000003
+                reduced[y, phase] = int(e.sum())
+            last = row1 == (height + 3) // 4
+            if phase == 0 and last:
+                err_out[:width] = (e[:width] * 7 + 1) % 1000003   # the alpha seed
+            else:
+                err_out[:n] = e
+
+    def fs_chain(ranges):
+        """what the chain must compute, sequentially"""
+        red = torch.zeros((height, 2), dtype=torch.int64)
+        fake, e_in, outs = FakeEnc(), None, None
+        for a, b in ranges:
+            outs = torch.zeros(3 * width, dtype=torch.int32)
+            fake.floyd_rows_device(torch.from_numpy(img[4 * a:4 * b].astype(np.int64)), width, height, 4, 1, a, b, 0, e_in, outs, red[4 * a:4 * b])
+            e_in = outs
+        e_in = outs[:width].clone()
+        for a, b in ranges:
+            outs = torch.zeros(width, dtype=torch.int32)
+            fake.floyd_rows_device(torch.from_numpy(img[4 * a:4 * b].astype(np.int64)), width, height, 4, 1, a, b, 1, e_in, outs, red[4 * a:4 * b])
+            e_in = outs
+        return red
+
+    ranges = [shard_block_rows(bh, world, r) for r in range(world)]
+    red = torch.zeros((4 * (row1 - row0), 2), dtype=torch.int64)
+    floyd_steinberg_sharded(FakeEnc(), dist, torch.from_numpy(mine.astype(np.int64)), width, height, 4, 1, row0, row1, rank, world, red,
+                            lambda n: torch.zeros(n, dtype=torch.int32))
+    assert torch.equal(red, fs_chain(ranges)[4 * row0:4 * row1]), ("floyd chain", rank)
     ret[rank] = True
     dist.destroy_process_group()
 
