@@ -81,6 +81,11 @@ struct s2tc_b200_ctx {
 	cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
 	std::mutex mu;
 	DevBuf src, reduced, out, ends, dither_ws, shard_ws, plans, small, mip, rand_ws;
+	// second lane (see encode_rows): with random candidates consecutive slabs run on two streams so that the tail of one
+	// search launch (its last one-warp CTAs, ~0.3 ms each, on a mostly idle GPU) overlaps the next slab's kernels
+	DevBuf reduced1, ends1, dither_ws1, rand_ws1, carries;
+	cudaStream_t aux = nullptr, aux2 = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_prepass = nullptr;
 	RandPlan *h_plans = nullptr; // pinned ring
 	int plan_next = 0;
 	int *h_carry = nullptr; // pinned, 4 ints
@@ -166,17 +171,18 @@ int settings_normalise(const s2tc_b200_settings *in, s2tc_b200_settings &s)
 
 // Encodes the blocks of `v` (a slab whose first block is block number blk0 of the image) into d_dst.
 int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &v, long long blk0, uint64_t cursor0,
-		void *d_dst, cudaStream_t st)
+		void *d_dst, cudaStream_t st, int lane = 0)
 {
 	const long long nblocks = view_blocks(v);
 	if (nblocks == 0)
 		return 0;
+	DevBuf &ends = lane ? c->ends1 : c->ends, &rand_ws = lane ? c->rand_ws1 : c->rand_ws;
 	if (v.images > 1 && s.nrandom > 0) { // the chunked rand() stream of the search kernel is per image: one image at a time
 		ImageView one = v;
 		one.images = 1;
 		for (int i = 0; i < v.images; ++i) {
 			one.base = v.base + (size_t) i * v.image_bytes;
-			if (int rc = encode_view(c, s, one, blk0, cursor0, (uint8_t *) d_dst + (size_t) i * v.out_image_bytes, st))
+			if (int rc = encode_view(c, s, one, blk0, cursor0, (uint8_t *) d_dst + (size_t) i * v.out_image_bytes, st, lane))
 				return rc;
 		}
 		return 0;
@@ -187,14 +193,14 @@ int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &
 		return 0;
 	}
 	const int nrandom = s.nrandom > 0 ? s.nrandom : 0;
-	CU(c->ends.reserve((size_t) nblocks * sizeof(uint2)));
+	CU(ends.reserve((size_t) nblocks * sizeof(uint2)));
 	if (nrandom == 0) { // <= 16 candidates: the register-resident search, then refinement + packing
 		{
 			FamScope f(c, st, kFamSearch, s.dxt == kDxt5 ? 2 : 1); // DXT5: colour launch + alpha launch
-			CU(launch_search16(s.dxt, s.cd, v, (uint2 *) c->ends.p, st));
+			CU(launch_search16(s.dxt, s.cd, v, (uint2 *) ends.p, st));
 		}
 		FamScope f(c, st, kFamFinish, 1);
-		CU(launch_finish(s.dxt, s.cd, s.refine, v, (const uint2 *) c->ends.p, d_dst, st));
+		CU(launch_finish(s.dxt, s.cd, s.refine, v, (const uint2 *) ends.p, d_dst, st));
 		return 0;
 	}
 	if (nrandom > pair_search_max_nrandom())
@@ -203,8 +209,11 @@ int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &
 	// jump polynomials for this slab: the warp that owns chunk t (kSearchChunkBlocks blocks) starts at
 	// cursor0 + (blk0 + kSearchChunkBlocks t) * draws_per_block
 	const uint64_t dpb = (uint64_t) draws_per_block(s.dxt, nrandom);
-	if (c->plan_next == kPlanRing) { // ring exhausted: wait for the uploads queued so far
+	if (c->plan_next == kPlanRing) { // ring exhausted: wait for the uploads queued so far (on either lane)
 		CU(cudaStreamSynchronize(st));
+		CU(cudaStreamSynchronize(c->aux));
+		CU(cudaStreamSynchronize(c->aux2));
+		CU(cudaStreamSynchronize(c->stream));
 		c->plan_next = 0;
 	}
 	RandPlan *hp = &c->h_plans[c->plan_next];
@@ -213,19 +222,19 @@ int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &
 	rand_plan_init(*hp, cursor0 + (uint64_t) blk0 * dpb, (uint64_t) kSearchChunkBlocks * dpb);
 	const RandPlan *hp_dev = nullptr;
 	CU(cudaHostGetDevicePointer((void **) &hp_dev, hp, 0));
-	CU(c->rand_ws.reserve(rand_windows_bytes((size_t) nblocks)));
+	CU(rand_ws.reserve(rand_windows_bytes((size_t) nblocks)));
 	{
 		FamScope f(c, st, kFamCand, 2);
 		CU(launch_plan_upload(hp_dev, dp, st));
-		CU(launch_rand_windows(dp, (unsigned) ((nblocks + kSearchChunkBlocks - 1) / kSearchChunkBlocks), (uint32_t *) c->rand_ws.p, st));
+		CU(launch_rand_windows(dp, (unsigned) ((nblocks + kSearchChunkBlocks - 1) / kSearchChunkBlocks), (uint32_t *) rand_ws.p, st));
 	}
 	{
 		FamScope f(c, st, kFamSearch, 1);
-		CU(launch_pair_search(s.dxt, s.cd, nrandom, v, (const uint32_t *) c->rand_ws.p, (uint2 *) c->ends.p, st));
+		CU(launch_pair_search(s.dxt, s.cd, nrandom, v, (const uint32_t *) rand_ws.p, (uint2 *) ends.p, st));
 	}
 	{
 		FamScope f(c, st, kFamFinish, 1);
-		CU(launch_finish(s.dxt, s.cd, s.refine, v, (const uint2 *) c->ends.p, d_dst, st));
+		CU(launch_finish(s.dxt, s.cd, s.refine, v, (const uint2 *) ends.p, d_dst, st));
 	}
 	return 0;
 }
@@ -234,8 +243,14 @@ int encode_view(s2tc_b200_ctx *c, const s2tc_b200_settings &s, const ImageView &
 // ready_ws: a dither workspace that already holds the chunk/tile maps of exactly these texels (phase 1 is skipped), or NULL.
 int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int width, int height,
 		const void *d_src_rows, int row0, int row1, void *d_dst, uint64_t cursor0, int *d_carry, cudaStream_t st,
-		void *ready_ws = nullptr, bool src_is_reduced = false)
+		void *ready_ws = nullptr, bool src_is_reduced = false, int lane = -1)
 {
+	// lane -1: everything on st with the first set of workspaces, except that with random candidates the slabs of the range
+	// alternate between st and the context's second stream (and workspace set) so that one search launch's tail overlaps
+	// the next slab; st waits for the second stream at the end.  lane 0 / 1: the caller pipelines ranges itself
+	// (compress_rows_host, the striped shards): this range uses workspace set `lane` on st, and ev_prepass is recorded on
+	// st when the 565 pre-pass (the only step that reads and writes the DITHER_SIMPLE carry) has been enqueued.
+	DevBuf &reduced = lane == 1 ? c->reduced1 : c->reduced, &dither_ws = lane == 1 ? c->dither_ws1 : c->dither_ws;
 	const int bh = (height + 3) / 4, bw = (width + 3) / 4;
 	if (width <= 0 || height <= 0 || row0 < 0 || row1 > bh || row0 > row1)
 		return fail(S2TC_B200_EINVAL, "bad geometry %dx%d rows [%d,%d)", width, height, row0, row1);
@@ -254,8 +269,8 @@ int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int
 		fmt = kSrcReduced;
 		texel_bytes = 4;
 	} else if (s.dither == kDitherSimple) {
-		CU(c->reduced.reserve(npix * 4));
-		CU(c->dither_ws.reserve(dither_workspace_bytes(npix)));
+		CU(reduced.reserve(npix * 4));
+		CU(dither_ws.reserve(dither_workspace_bytes(npix)));
 		int *carry = d_carry;
 		if (!carry) {
 			carry = (int *) c->small.p;
@@ -263,35 +278,53 @@ int encode_rows(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int srccomps, int
 		}
 		const bool ready = ready_ws != nullptr;
 		FamScope f(c, st, kFamPrepass, prepass_simple_launches(npix, ready));
-		CU(launch_prepass_simple(d_src_rows, comps, abits, npix, c->reduced.p, carry, ready ? ready_ws : c->dither_ws.p, ready, st));
-		texels = (const uint8_t *) c->reduced.p;
+		CU(launch_prepass_simple(d_src_rows, comps, abits, npix, reduced.p, carry, ready ? ready_ws : dither_ws.p, ready, st));
+		texels = (const uint8_t *) reduced.p;
 		fmt = kSrcReduced;
 		texel_bytes = 4;
 	} else if (s.dither == kDitherFloyd) {
 		if (row0 != 0 || row1 != bh)
 			return fail(S2TC_B200_EUNSUPPORTED, "DITHER_FLOYDSTEINBERG diffuses error between rows: encode the whole image in one call "
 					"(block rows [%d,%d) of %d requested)", row0, row1, bh);
-		CU(c->reduced.reserve(npix * 4));
-		CU(c->dither_ws.reserve(floyd_workspace_bytes(width, height)));
+		CU(reduced.reserve(npix * 4));
+		CU(dither_ws.reserve(floyd_workspace_bytes(width, height)));
 		FamScope f(c, st, kFamPrepass, comps == 4 && abits != 8 ? 2 : 1);
-		CU(launch_prepass_floyd(d_src_rows, comps, abits, width, height, c->reduced.p, c->dither_ws.p, st));
-		texels = (const uint8_t *) c->reduced.p;
+		CU(launch_prepass_floyd(d_src_rows, comps, abits, width, height, reduced.p, dither_ws.p, st));
+		texels = (const uint8_t *) reduced.p;
 		fmt = kSrcReduced;
 		texel_bytes = 4;
 	}
+	if (lane >= 0)
+		CU(cudaEventRecord(c->ev_prepass, st));
 
 	// MODE_NORMAL goes slab by slab to bound the candidate/endpoint workspaces
 	// only the random-candidate path has per-block workspaces to bound; the fused kernels take the range in one launch
 	const bool one_launch = s.nrandom <= 0;
 	long long rows_per_slab = one_launch ? (row1 - row0) : (kSlabBlocks / bw > 0 ? kSlabBlocks / bw : 1);
 	const int bs = block_bytes(s.dxt);
-	for (long long r = row0; r < row1; r += rows_per_slab) {
-		const int r1 = (int) (r + rows_per_slab < row1 ? r + rows_per_slab : row1);
+	// two lanes inside this range?  (not while per-family times are being taken: they assume one stream)
+	const bool alternate = lane < 0 && !one_launch && (row1 - row0) >= rows_per_slab + rows_per_slab / 2 && !c->profiling && st != c->aux;
+	if (alternate) {
+		CU(cudaEventRecord(c->ev_fork, st));
+		CU(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
+	}
+	int k = 0;
+	for (long long r = row0, rnext; r < row1; r = rnext, ++k) {
+		int r1 = (int) (r + rows_per_slab < row1 ? r + rows_per_slab : row1);
+		if (row1 - r1 < rows_per_slab / 2)
+			r1 = row1; // a small remainder joins this slab: every launch of the search kernel costs a tail (compress_rows_host)
 		const int sy0 = (int) r * 4 - y0, sy1 = (r1 * 4 < height ? r1 * 4 : height) - y0;
 		const ImageView v = make_view(texels + (size_t) sy0 * width * texel_bytes, width, sy1 - sy0, fmt, abits);
-		int rc = encode_view(c, s, v, (long long) r * bw, cursor0, (uint8_t *) d_dst + (size_t) (r - row0) * bw * bs, st);
+		const int l = alternate ? (k & 1) : (lane == 1 ? 1 : 0);
+		int rc = encode_view(c, s, v, (long long) r * bw, cursor0, (uint8_t *) d_dst + (size_t) (r - row0) * bw * bs,
+				alternate && l ? c->aux : st, l);
 		if (rc)
 			return rc;
+		rnext = r1;
+	}
+	if (alternate) {
+		CU(cudaEventRecord(c->ev_join, c->aux));
+		CU(cudaStreamWaitEvent(st, c->ev_join, 0));
 	}
 	return 0;
 }
@@ -334,6 +367,12 @@ int s2tc_b200_ctx_create(int device, s2tc_b200_ctx **out)
 		CU(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
 		CU(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
 		CU(cudaEventCreateWithFlags(&c->last_done, cudaEventDisableTiming));
+		CU(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+		CU(cudaStreamCreateWithFlags(&c->aux2, cudaStreamNonBlocking));
+		CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+		CU(cudaEventCreateWithFlags(&c->ev_prepass, cudaEventDisableTiming));
+		CU(c->carries.reserve(4 * sizeof(int) * 256));
 		CU(cudaHostAlloc((void **) &c->h_plans, sizeof(RandPlan) * kPlanRing, cudaHostAllocMapped));
 		CU(cudaHostAlloc((void **) &c->h_carry, 4 * sizeof(int), cudaHostAllocDefault));
 		CU(cudaHostAlloc((void **) &c->h_summary, 16 * sizeof(uint64_t), cudaHostAllocDefault));
@@ -364,7 +403,8 @@ void s2tc_b200_ctx_destroy(s2tc_b200_ctx *c)
 		cudaEventDestroy(p.a);
 		cudaEventDestroy(p.b);
 	}
-	DevBuf *bufs[] = {&c->src, &c->reduced, &c->out, &c->ends, &c->dither_ws, &c->shard_ws, &c->plans, &c->small, &c->mip, &c->rand_ws};
+	DevBuf *bufs[] = {&c->src, &c->reduced, &c->out, &c->ends, &c->dither_ws, &c->shard_ws, &c->plans, &c->small, &c->mip, &c->rand_ws,
+			&c->reduced1, &c->ends1, &c->dither_ws1, &c->rand_ws1, &c->carries};
 	for (DevBuf *b : bufs)
 		b->release();
 	cudaFreeHost(c->h_plans);
@@ -373,6 +413,13 @@ void s2tc_b200_ctx_destroy(s2tc_b200_ctx *c)
 	cudaFreeHost(c->h_block);
 	if (c->last_done)
 		cudaEventDestroy(c->last_done);
+	for (cudaEvent_t e : {c->ev_fork, c->ev_join, c->ev_prepass})
+		if (e)
+			cudaEventDestroy(e);
+	if (c->aux)
+		cudaStreamDestroy(c->aux);
+	if (c->aux2)
+		cudaStreamDestroy(c->aux2);
 	if (c->stream)
 		cudaStreamDestroy(c->stream);
 	if (c->copy_in)
@@ -642,6 +689,10 @@ int compress_rows_host(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int comps,
 	std::vector<size_t> ws_off(nslab + 1, 0);
 	cudaEvent_t t0 = nullptr;
 	const bool pipelined = nslab > 1 || exchange;
+	// random candidates: consecutive slabs alternate between the compute stream and the context's second stream (each with
+	// its own workspaces), so that the tail of one slab's search launch overlaps the next slab's kernels; the DITHER_SIMPLE
+	// carry still goes from slab to slab in order (every pre-pass waits for the one before it)
+	const bool lanes = s.nrandom > 0 && nslab > 1 && !exchange && !c->profiling && st != c->aux && s.dither != kDitherFloyd;
 	auto slab_rows = [&](int i, int &r0, int &r1) {
 		if (first_rows > 0) { // growing slabs
 			long long a = 0, sz = first_rows;
@@ -680,6 +731,8 @@ int compress_rows_host(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int comps,
 			}
 		}
 		cudaStream_t sin_ = pipelined ? c->copy_in : st, sout = pipelined ? c->copy_out : st;
+		if (lanes) // the second lane starts behind whatever the compute stream was given before this call, too
+			CU(cudaStreamWaitEvent(c->aux, t0, 0));
 		if (exchange) { // phase A: upload + summarise slab by slab
 			for (int i = 0; i < nslab; ++i) {
 				int r0, r1;
@@ -714,19 +767,22 @@ int compress_rows_host(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int comps,
 			size_t off, len;
 			slab_rows(i, r0, r1);
 			slab_texels(r0, r1, off, len);
+			cudaStream_t sl = lanes && (i & 1) ? c->aux : st; // this slab's stream
 			if (!exchange) {
 				CU(cudaMemcpyAsync((uint8_t *) c->src.p + off, src_rows + off, len, cudaMemcpyHostToDevice, sin_));
 				if (pipelined || trace) {
 					CU(cudaEventRecord(up[i], sin_));
-					CU(cudaStreamWaitEvent(st, up[i], 0));
+					CU(cudaStreamWaitEvent(sl, up[i], 0));
 				}
 			}
+			if (lanes && i > 0 && s.dither == kDitherSimple)
+				CU(cudaStreamWaitEvent(sl, c->ev_prepass, 0)); // the carry leaving slab i - 1
 			uint8_t *d_out = (uint8_t *) c->out.p + (size_t) (r0 - row0) * tight;
-			if (int e = encode_rows(c, s, comps, width, height, (const uint8_t *) c->src.p + off, r0, r1, d_out, cursor, d_carry, st,
-						exchange ? (uint8_t *) c->shard_ws.p + ws_off[i] : nullptr))
+			if (int e = encode_rows(c, s, comps, width, height, (const uint8_t *) c->src.p + off, r0, r1, d_out, cursor, d_carry, sl,
+						exchange ? (uint8_t *) c->shard_ws.p + ws_off[i] : nullptr, false, lanes ? (i & 1) : -1))
 				return e;
 			if (pipelined || trace) {
-				CU(cudaEventRecord(done[i], st));
+				CU(cudaEventRecord(done[i], sl));
 				CU(cudaStreamWaitEvent(sout, done[i], 0));
 			}
 			if (row_bytes == tight)
@@ -738,7 +794,10 @@ int compress_rows_host(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int comps,
 		}
 		return 0;
 	}();
-	const cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(c->copy_in), e3 = cudaStreamSynchronize(c->copy_out);
+	cudaError_t e1 = cudaStreamSynchronize(st);
+	const cudaError_t e2 = cudaStreamSynchronize(c->copy_in), e3 = cudaStreamSynchronize(c->copy_out), e4 = cudaStreamSynchronize(c->aux);
+	if (e1 == cudaSuccess)
+		e1 = e4;
 	if (trace && !rc && e1 == cudaSuccess && e2 == cudaSuccess && e3 == cudaSuccess) {
 		for (int i = 0; i < nslab; ++i) {
 			float a = 0, b = 0, d = 0;
@@ -970,8 +1029,12 @@ int s2tc_b200_compress_host_striped(s2tc_b200_ctx *c, const s2tc_b200_settings *
 	CU(c->out.reserve(out_total ? out_total : 1));
 	if (ws_total)
 		CU(c->shard_ws.reserve(ws_total));
-	int *d_carry = simple ? (int *) c->small.p + 8 : nullptr;  // carry entering the current stripe
 	int *d_wave = (int *) c->small.p + 24;                     // carry entering the current wave's first stripe
+	// The control work of every wave (summary, all-gather, folds) runs on st.  With random candidates the stripes themselves
+	// alternate between the context's two lane streams, each behind its wave's control work, so that the tail of one
+	// stripe's search launch overlaps the next stripe (compress_rows_host) and the control work of wave w + 1 does not wait
+	// for the kernels of wave w.  Every stripe has its own carry slot: fold(w + 1) must not overwrite what encode(w) reads.
+	const bool lanes = s.nrandom > 0 && nwave > 1 && !c->profiling && st != c->aux && st != c->aux2;
 	ByteMap *d_mine = (ByteMap *) d_maps_mine, *d_all = (ByteMap *) d_maps_all;
 	std::vector<cudaEvent_t> up(nwave, nullptr), done(nwave, nullptr);
 	cudaEvent_t t0 = nullptr;
@@ -985,7 +1048,7 @@ int s2tc_b200_compress_host_striped(s2tc_b200_ctx *c, const s2tc_b200_settings *
 		CU(cudaStreamWaitEvent(c->copy_in, t0, 0));
 		CU(cudaStreamWaitEvent(c->copy_out, t0, 0));
 		if (simple)
-			CU(cudaMemsetAsync(exchange ? d_wave : d_carry, 0, 4 * sizeof(int), st));
+			CU(cudaMemsetAsync(exchange ? d_wave : (int *) c->small.p + 8, 0, 4 * sizeof(int), st));
 		for (int w = 0; w < nwave; ++w) { // all uploads are queued at once; the compute stream takes them as they land
 			if (sp[w].in_len)
 				CU(cudaMemcpyAsync((uint8_t *) c->src.p + sp[w].in_off, src_stripes[w], sp[w].in_len, cudaMemcpyHostToDevice, c->copy_in));
@@ -996,6 +1059,7 @@ int s2tc_b200_compress_host_striped(s2tc_b200_ctx *c, const s2tc_b200_settings *
 			const uint8_t *d_in = (const uint8_t *) c->src.p + q.in_off;
 			uint8_t *ws = ws_total ? (uint8_t *) c->shard_ws.p + q.ws_off : nullptr;
 			CU(cudaStreamWaitEvent(st, up[w], 0));
+			int *d_carry = simple ? (exchange ? (int *) c->carries.p + 4 * w : (int *) c->small.p + 8) : nullptr; // carry entering this stripe
 			if (exchange) {
 				{
 					FamScope f(c, st, kFamPrepass, q.in_len ? kDitherSummaryLaunches : 1);
@@ -1012,16 +1076,29 @@ int s2tc_b200_compress_host_striped(s2tc_b200_ctx *c, const s2tc_b200_settings *
 			}
 			if (q.r1 > q.r0) {
 				uint8_t *d_out = (uint8_t *) c->out.p + q.out_off;
-				if (int e = encode_rows(c, s, comps, width, height, d_in, q.r0, q.r1, d_out, rand_cursor0, d_carry, st, exchange ? ws : nullptr))
+				cudaStream_t sl = st;
+				if (lanes) { // behind this wave's upload and folds
+					sl = (w & 1) ? c->aux : c->aux2;
+					CU(cudaEventRecord(c->ev_fork, st));
+					CU(cudaStreamWaitEvent(sl, c->ev_fork, 0));
+				}
+				if (lanes && w > 0 && simple && !exchange)
+					CU(cudaStreamWaitEvent(sl, c->ev_prepass, 0)); // one shard: the carry is chained from stripe to stripe
+				if (int e = encode_rows(c, s, comps, width, height, d_in, q.r0, q.r1, d_out, rand_cursor0, d_carry, sl, exchange ? ws : nullptr,
+							false, lanes ? (w & 1) : -1))
 					return e;
-				CU(cudaEventRecord(done[w], st));
+				CU(cudaEventRecord(done[w], sl));
 				CU(cudaStreamWaitEvent(c->copy_out, done[w], 0));
 				CU(cudaMemcpyAsync(dest_stripes[w], d_out, q.out_len, cudaMemcpyDeviceToHost, c->copy_out));
 			}
 		}
 		return 0;
 	}();
-	const cudaError_t e1 = cudaStreamSynchronize(st), e2 = cudaStreamSynchronize(c->copy_in), e3 = cudaStreamSynchronize(c->copy_out);
+	cudaError_t e1 = cudaStreamSynchronize(st);
+	const cudaError_t e2 = cudaStreamSynchronize(c->copy_in), e3 = cudaStreamSynchronize(c->copy_out);
+	const cudaError_t e4 = cudaStreamSynchronize(c->aux), e5 = cudaStreamSynchronize(c->aux2);
+	if (e1 == cudaSuccess)
+		e1 = e4 != cudaSuccess ? e4 : e5;
 	for (int w = 0; w < nwave; ++w) {
 		if (up[w])
 			cudaEventDestroy(up[w]);

@@ -42,7 +42,10 @@ def floyd_steinberg_sharded(enc, dist, src_rows, width, height, comps, alphabits
     (s2tc_algorithm.cpp:1380,1397), so the seed travels from the last rank to rank 0 and the alpha pass goes down the same
     way.  dist: torch.distributed (send / recv on the current stream) or anything with the same two calls;
     new_ints(n): a zeroed int32 buffer of n elements on the device the exchange uses.  Writes reduced_rows (4 bytes per
-    texel), to be encoded with Encoder.encode_reduced_rows_device."""
+    texel), to be encoded with Encoder.encode_reduced_rows_device.
+    Everything is asynchronous on `stream`, which must be the stream `dist` and `new_ints` work on (torch's current stream);
+    the exchange buffers are returned and must be kept alive until the stream has finished with them -- if they are
+    allocated on another stream, a caching allocator may hand their memory out again while the kernels still use it."""
     if row1 <= row0:
         raise ValueError("Floyd-Steinberg shards must not be empty")
     err_in, err_out = new_ints(3 * width), new_ints(3 * width)
@@ -53,7 +56,7 @@ def floyd_steinberg_sharded(enc, dist, src_rows, width, height, comps, alphabits
     if rank < world - 1:
         dist.send(err_out, dst=rank + 1)
     if comps != 4 or alphabits == 8:
-        return
+        return err_in, err_out
     seed, a_out = new_ints(width), new_ints(width)
     if world == 1:
         seed = err_out[:width]
@@ -66,3 +69,4 @@ def floyd_steinberg_sharded(enc, dist, src_rows, width, height, comps, alphabits
     enc.floyd_rows_device(src_rows, width, height, comps, alphabits, row0, row1, 1, seed, a_out, reduced_rows, stream=stream)
     if rank < world - 1:
         dist.send(a_out, dst=rank + 1)
+    return err_in, err_out, seed, a_out

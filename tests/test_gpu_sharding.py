@@ -183,8 +183,14 @@ def test_floyd_steinberg_row_shards_equal_whole_image(dxt, comps, world, width, 
             rows = d_img[4 * a:min(4 * b, height)].contiguous()
             reduced = torch.zeros(rows.shape[0] * width, dtype=torch.int32, device="cuda")
             torch.cuda.synchronize()
-            floyd_steinberg_sharded(enc, qd.view(rank), rows, width, height, comps, abits, a, b, rank, world, reduced,
-                                    lambda n: torch.zeros(n, dtype=torch.int32, device="cuda"))
+            def new_ints(n):             # torch fills on ITS stream; the encoder runs on its own: finish the fill first
+                t = torch.zeros(n, dtype=torch.int32, device="cuda")
+                torch.cuda.synchronize()
+                return t
+
+            keep = floyd_steinberg_sharded(enc, qd.view(rank), rows, width, height, comps, abits, a, b, rank, world, reduced, new_ints)
+            enc.sync()                   # the exchange buffers were allocated on torch's stream: keep them until the encoder is done
+            del keep
             d_out = torch.zeros((b - a) * bw * bs, dtype=torch.uint8, device="cuda")
             torch.cuda.synchronize()
             enc.encode_reduced_rows_device(reduced, width, height, a, b, d_out, st)
