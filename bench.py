@@ -209,6 +209,9 @@ def search_ops(hist, nrandom, dxt, cd_n):
 
 
 def main():
+    if os.environ.get("S2TC_BENCH_WATCHDOG"):   # debugging aid: dump every thread's Python stack to stderr if the run takes too long
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["S2TC_BENCH_WATCHDOG"]), repeat=True, file=sys.stderr)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -7,8 +7,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.cuh"
@@ -76,6 +79,114 @@ constexpr long long kSlabBlocks = 1 << 22; // MODE_NORMAL works through an image
 
 } // namespace
 
+namespace {
+
+// Host-side copies between the caller's pageable memory and the pinned staging buffers, on a few threads: one memcpy
+// thread moves ~10 GB/s, the PCIe link takes ~50.  (The driver's own pageable path stages on the calling thread:
+// tx_compress_dxtn on malloc'd memory took 145 ms for config 3 against 42 ms from pinned memory.)
+class CopyPool {
+public:
+	static CopyPool &get()
+	{
+		// never destroyed: its threads wait on the condition variable for the life of the process, and destroying a
+		// condition variable with waiters blocks (the process would hang in its exit handlers)
+		static CopyPool *pool = new CopyPool;
+		return *pool;
+	}
+	void copy(void *dst, const void *src, size_t n)
+	{
+		const size_t nth = workers_.size() + 1;
+		if (n < (1u << 20) || nth == 1) {
+			memcpy(dst, src, n);
+			return;
+		}
+		std::unique_lock<std::mutex> call(call_mu_); // one parallel copy at a time
+		const size_t part = ((n + nth - 1) / nth + 4095) & ~(size_t) 4095;
+		{
+			std::lock_guard<std::mutex> lk(mu_);
+			dst_ = (uint8_t *) dst;
+			src_ = (const uint8_t *) src;
+			n_ = n;
+			part_ = part;
+			pending_ = (int) workers_.size();
+			++gen_;
+		}
+		cv_.notify_all();
+		run_part(0, (uint8_t *) dst, (const uint8_t *) src, n, part);
+		std::unique_lock<std::mutex> lk(mu_);
+		done_cv_.wait(lk, [&] { return pending_ == 0; });
+	}
+
+private:
+	CopyPool()
+	{
+		const char *e = getenv("S2TC_B200_COPY_THREADS");
+		int n = e ? atoi(e) : 0;
+		if (n <= 0) {
+			const unsigned hw = std::thread::hardware_concurrency();
+			n = hw >= 16 ? 8 : (hw >= 4 ? (int) hw / 2 : 1);
+		}
+		for (int i = 1; i < n; ++i)
+			workers_.emplace_back([this, i] { loop(i); });
+		for (auto &t : workers_)
+			t.detach(); // live for the life of the process (the library has no teardown call, like the reference's)
+	}
+	static void run_part(size_t idx, uint8_t *dst, const uint8_t *src, size_t n, size_t part)
+	{
+		const size_t a = idx * part;
+		if (a < n)
+			memcpy(dst + a, src + a, n - a < part ? n - a : part);
+	}
+	void loop(int idx)
+	{
+		uint64_t seen = 0;
+		for (;;) {
+			uint8_t *dst;
+			const uint8_t *src;
+			size_t n, part;
+			{
+				std::unique_lock<std::mutex> lk(mu_);
+				cv_.wait(lk, [&] { return gen_ != seen; });
+				seen = gen_;
+				dst = dst_;
+				src = src_;
+				n = n_;
+				part = part_;
+			}
+			run_part((size_t) idx, dst, src, n, part);
+			{
+				std::lock_guard<std::mutex> lk(mu_);
+				--pending_;
+			}
+			done_cv_.notify_one();
+		}
+	}
+	std::vector<std::thread> workers_;
+	std::mutex mu_, call_mu_;
+	std::condition_variable cv_, done_cv_;
+	uint8_t *dst_ = nullptr;
+	const uint8_t *src_ = nullptr;
+	size_t n_ = 0, part_ = 0;
+	int pending_ = 0;
+	uint64_t gen_ = 0;
+};
+
+// page-locked (cudaHostAlloc / cudaHostRegister) or managed: the DMA engines can read / write it directly
+bool host_pinned(const void *p)
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+		cudaGetLastError();
+		return false;
+	}
+	return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+constexpr size_t kStageChunk = (size_t) 8 << 20; // staging granularity of pageable uploads
+constexpr int kStageSlots = 4;
+
+} // namespace
+
 struct s2tc_b200_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
@@ -85,6 +196,10 @@ struct s2tc_b200_ctx {
 	// search launch (its last one-warp CTAs, ~0.3 ms each, on a mostly idle GPU) overlaps the next slab's kernels
 	DevBuf reduced1, ends1, dither_ws1, rand_ws1, carries;
 	cudaStream_t aux = nullptr, aux2 = nullptr;
+	// pageable caller memory is staged through these (allocated on first use)
+	uint8_t *h_stage_in = nullptr, *h_stage_out = nullptr;
+	size_t h_stage_out_cap = 0;
+	cudaEvent_t stage_ev[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_prepass = nullptr;
 	RandPlan *h_plans = nullptr; // pinned ring
 	int plan_next = 0;
@@ -411,6 +526,13 @@ void s2tc_b200_ctx_destroy(s2tc_b200_ctx *c)
 	cudaFreeHost(c->h_carry);
 	cudaFreeHost(c->h_summary);
 	cudaFreeHost(c->h_block);
+	if (c->h_stage_in)
+		cudaFreeHost(c->h_stage_in);
+	if (c->h_stage_out)
+		cudaFreeHost(c->h_stage_out);
+	for (cudaEvent_t e : c->stage_ev)
+		if (e)
+			cudaEventDestroy(e);
 	if (c->last_done)
 		cudaEventDestroy(c->last_done);
 	for (cudaEvent_t e : {c->ev_fork, c->ev_join, c->ev_prepass})
@@ -693,6 +815,29 @@ int compress_rows_host(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int comps,
 	// its own workspaces), so that the tail of one slab's search launch overlaps the next slab's kernels; the DITHER_SIMPLE
 	// carry still goes from slab to slab in order (every pre-pass waits for the one before it)
 	const bool lanes = s.nrandom > 0 && nslab > 1 && !exchange && !c->profiling && st != c->aux && s.dither != kDitherFloyd;
+	// Pageable caller memory (what Mesa and the reference's own tool pass to tx_compress_dxtn): the driver would stage it on
+	// this thread, slab after slab, at a fraction of the link's speed and without overlapping anything.  Instead the texels
+	// go through a ring of pinned chunks filled by a few copy threads while the GPU works on the previous slab, and the
+	// blocks come back through a pinned buffer and are copied out as their slabs finish.
+	static const bool no_stage = getenv("S2TC_B200_NO_STAGING") && atoi(getenv("S2TC_B200_NO_STAGING"));
+	const bool stage_in = !exchange && !no_stage && in_bytes >= ((size_t) 1 << 20) && !host_pinned(src_rows);
+	const bool stage_out = !exchange && !no_stage && row_bytes == tight && out_bytes >= ((size_t) 1 << 18) && !host_pinned(dest);
+	if (stage_in && !c->h_stage_in) {
+		CU(cudaHostAlloc((void **) &c->h_stage_in, kStageChunk * kStageSlots, cudaHostAllocDefault));
+		for (int k = 0; k < kStageSlots; ++k)
+			CU(cudaEventCreateWithFlags(&c->stage_ev[k], cudaEventDisableTiming));
+	}
+	if (stage_out && c->h_stage_out_cap < out_bytes) {
+		if (c->h_stage_out)
+			cudaFreeHost(c->h_stage_out);
+		c->h_stage_out = nullptr;
+		c->h_stage_out_cap = 0;
+		CU(cudaHostAlloc((void **) &c->h_stage_out, out_bytes, cudaHostAllocDefault));
+		c->h_stage_out_cap = out_bytes;
+	}
+	std::vector<cudaEvent_t> landed(stage_out ? nslab : 0, nullptr); // slab i's blocks are in the pinned output buffer
+	int drained = 0;                                               // slabs [0, drained) have been copied to dest
+	size_t staged_chunks = 0;
 	auto slab_rows = [&](int i, int &r0, int &r1) {
 		if (first_rows > 0) { // growing slabs
 			long long a = 0, sz = first_rows;
@@ -769,7 +914,20 @@ int compress_rows_host(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int comps,
 			slab_texels(r0, r1, off, len);
 			cudaStream_t sl = lanes && (i & 1) ? c->aux : st; // this slab's stream
 			if (!exchange) {
-				CU(cudaMemcpyAsync((uint8_t *) c->src.p + off, src_rows + off, len, cudaMemcpyHostToDevice, sin_));
+				if (stage_in) { // chunk by chunk through the pinned ring; this thread and the pool do the copying
+					for (size_t o = 0; o < len; o += kStageChunk, ++staged_chunks) {
+						const size_t n = len - o < kStageChunk ? len - o : kStageChunk;
+						const int slot = (int) (staged_chunks % kStageSlots);
+						if (staged_chunks >= (size_t) kStageSlots)
+							CU(cudaEventSynchronize(c->stage_ev[slot])); // the chunk that used this slot is on the device
+						uint8_t *h = c->h_stage_in + (size_t) slot * kStageChunk;
+						CopyPool::get().copy(h, src_rows + off + o, n);
+						CU(cudaMemcpyAsync((uint8_t *) c->src.p + off + o, h, n, cudaMemcpyHostToDevice, sin_));
+						CU(cudaEventRecord(c->stage_ev[slot], sin_));
+					}
+				} else {
+					CU(cudaMemcpyAsync((uint8_t *) c->src.p + off, src_rows + off, len, cudaMemcpyHostToDevice, sin_));
+				}
 				if (pipelined || trace) {
 					CU(cudaEventRecord(up[i], sin_));
 					CU(cudaStreamWaitEvent(sl, up[i], 0));
@@ -785,15 +943,38 @@ int compress_rows_host(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int comps,
 				CU(cudaEventRecord(done[i], sl));
 				CU(cudaStreamWaitEvent(sout, done[i], 0));
 			}
-			if (row_bytes == tight)
+			if (stage_out) {
+				CU(cudaMemcpyAsync(c->h_stage_out + (size_t) (r0 - row0) * tight, d_out, (size_t) (r1 - r0) * tight, cudaMemcpyDeviceToHost, sout));
+				CU(cudaEventCreateWithFlags(&landed[i], cudaEventDisableTiming));
+				CU(cudaEventRecord(landed[i], sout));
+				while (drained < i) { // finished slabs leave while we are here anyway
+					if (cudaEventQuery(landed[drained]) != cudaSuccess) {
+						cudaGetLastError(); // "not ready" is not an error
+						break;
+					}
+					int a0, a1;
+					slab_rows(drained, a0, a1);
+					CopyPool::get().copy(dest + (size_t) (a0 - row0) * tight, c->h_stage_out + (size_t) (a0 - row0) * tight, (size_t) (a1 - a0) * tight);
+					++drained;
+				}
+			} else if (row_bytes == tight)
 				CU(cudaMemcpyAsync(dest + (size_t) (r0 - row0) * tight, d_out, (size_t) (r1 - r0) * tight, cudaMemcpyDeviceToHost, sout));
 			else if (row_bytes > tight)
 				CU(cudaMemcpy2DAsync(dest + (size_t) (r0 - row0) * row_bytes, row_bytes, d_out, tight, tight, r1 - r0, cudaMemcpyDeviceToHost, sout));
 			if (trace)
 				CU(cudaEventRecord(down[i], sout));
 		}
+		for (; stage_out && drained < nslab; ++drained) { // the rest, in order, each as soon as it has landed
+			int a0, a1;
+			slab_rows(drained, a0, a1);
+			CU(cudaEventSynchronize(landed[drained]));
+			CopyPool::get().copy(dest + (size_t) (a0 - row0) * tight, c->h_stage_out + (size_t) (a0 - row0) * tight, (size_t) (a1 - a0) * tight);
+		}
 		return 0;
 	}();
+	for (cudaEvent_t e : landed)
+		if (e)
+			cudaEventDestroy(e);
 	cudaError_t e1 = cudaStreamSynchronize(st);
 	const cudaError_t e2 = cudaStreamSynchronize(c->copy_in), e3 = cudaStreamSynchronize(c->copy_out), e4 = cudaStreamSynchronize(c->aux);
 	if (e1 == cudaSuccess)

@@ -251,3 +251,29 @@ def test_summary_maps_are_not_reused_after_the_texels_changed(encoder):
         encoder.encode_rows_device(d, 512, 256, 4, 0, 64, out, st, stream=stream.cuda_stream)
         stream.synchronize()
     assert np.array_equal(out.cpu().numpy(), O.orc_compress(b, O.DXT1, O.WAVG, -1, O.ALWAYS, O.DITHER_SIMPLE))
+
+
+@pytest.mark.parametrize("dxt,cd,nr,rf,dither", [(O.DXT1, O.WAVG, -1, O.ALWAYS, O.DITHER_SIMPLE), (O.DXT5, O.SRGB_MIXED, 0, O.LOOP, O.DITHER_SIMPLE),
+                                                 (O.DXT1, O.WAVG, 7, O.LOOP, O.DITHER_SIMPLE), (O.DXT3, O.RGB, -1, O.NEVER, O.DITHER_NONE)])
+def test_pageable_buffers_are_staged(encoder, dxt, cd, nr, rf, dither):
+    """Large malloc'd source and destination (what tx_compress_dxtn's callers pass): the texels travel through the pinned
+    staging ring in 8 MiB chunks filled by the copy threads, the blocks come back through the pinned output buffer.  Same
+    bytes as from pinned memory; first and last block rows against the oracle; 3-component source; the staging switch."""
+    import torch
+    from s2tc_b200 import Settings
+    width, height = 4096, 2500 if nr <= 0 else 1100   # 39 MiB / 17 MiB of texels: several chunks, the last one partial
+    img = synth.synth_rgba(width, height, seed=61)
+    st = Settings(dxt, cd, nr, rf, dither)
+    bw, bs = (width + 3) // 4, O.block_bytes(dxt)
+    got = encoder.compress(img, st, cursor=5)                       # numpy in, numpy out: pageable both ways
+    pinned_src = torch.from_numpy(img).pin_memory()
+    pinned_dst = torch.empty(got.size, dtype=torch.uint8).pin_memory()
+    encoder.compress(pinned_src, st, cursor=5, out=pinned_dst)
+    assert np.array_equal(got, pinned_dst.numpy())
+    bh = (height + 3) // 4
+    for a, b in ((0, 2), (bh - 2, bh)):
+        want = O.orc_rows(img, dxt, cd, nr, rf, dither, (a, b), cursor=5)
+        assert np.array_equal(got[a * bw * bs:b * bw * bs], want), (a, b)
+    rgb = np.ascontiguousarray(img[:1000, :, :3])                   # 12 MiB, 3 components
+    if nr < 0:
+        assert np.array_equal(encoder.compress(rgb, st, cursor=5), O.orc_compress(rgb, dxt, cd, nr, rf, dither, cursor=5))
