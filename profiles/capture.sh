@@ -9,10 +9,10 @@ OUT=gpurun_out/profiles_$TAG
 mkdir -p $OUT
 NCU="ncu --clock-control none"
 launches() { # name, bench args
-	$NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $OUT/launches_$1.csv python bench.py ${@:2} --steps 2 --kernel-only --no-check > /dev/null 2>&1
+	timeout 240 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $OUT/launches_$1.csv python bench.py ${@:2} --steps 2 --kernel-only --no-check > /dev/null 2>&1
 }
 full() { # name, kernel regex, skip, count, bench args
-	$NCU --set full --import-source on -k regex:"$2" -s $3 -c $4 -f -o /tmp/prof_$1 python bench.py ${@:5} --steps 1 --kernel-only --no-check > /dev/null 2>&1
+	timeout 300 $NCU --set full --import-source on -k regex:"$2" -s $3 -c $4 -f -o /tmp/prof_$1 python bench.py ${@:5} --steps 1 --kernel-only --no-check > /dev/null 2>&1
 	python profiles/ncu_summary.py /tmp/prof_$1.ncu-rep > $OUT/$1.ncu.txt 2>&1
 	python profiles/ncu_source.py /tmp/prof_$1.ncu-rep 32 > $OUT/$1.source.txt 2>&1
 	rm -f /tmp/prof_$1.ncu-rep
