@@ -562,6 +562,7 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, int sadj, uint32_t one, c
 			bx = 0;
 			++by;
 		}
+		__syncwarp(); // the previous block's reads of `texels` (a single-colour block leaves the loop body without another barrier)
 		if (lane < 4) {
 			*reinterpret_cast<uint4 *>(texels + lane * 4) = make_uint4(nextrow[0], nextrow[1], nextrow[2], nextrow[3]);
 			if (bi + 1 < nb)
