@@ -30,7 +30,7 @@ constexpr int kSearchThreads = 32; // one warp per CTA: a CTA slot frees as soon
 constexpr int kSearchWarps = kSearchThreads / 32;
 constexpr int kPitch16 = 8;  // words per row, 16-bit distances: rows are only read whole (quantisation, exact sums of survivors)
 constexpr int kPitch32 = 20; // words per row, 32-bit distances (16 used)
-constexpr int kListCap = 288; // survivor groups waiting for their exact sums: < 8 carried over + at most 128 from one pass of two tile columns
+constexpr int kListCap = 160; // survivor groups waiting for their exact sums: < 8 carried over + at most 128 from one pass of two tile columns
 constexpr uint32_t kFlushGroups = 8; // 8 groups = 32 pairs = one exact sum per lane
 #ifndef S2TC_PS_FLUSH
 #define S2TC_PS_FLUSH 0
@@ -41,16 +41,19 @@ constexpr uint32_t kFlushGroups = 8; // 8 groups = 32 pairs = one exact sum per 
 #ifndef S2TC_PS_MINCTAS
 #define S2TC_PS_MINCTAS 32
 #endif
+#ifndef S2TC_PS_PREFETCH
+#define S2TC_PS_PREFETCH 0 // 1: the next block's rand() draws are generated inside this block's tile loop (measured slower, see pair_search_kernel)
+#endif
 constexpr int kRing = 256;    // rand() outputs kept per warp (a batch of 32 candidates needs <= 128 + 61)
 
 template <int CD> struct Packs16 { static constexpr bool value = CD == kAVG || CD == kWAVG || CD == kW0AVG; };
 
-// per-warp shared memory, byte offsets (all multiples of 16).  Two regions are used twice: the rand() ring lives where the
-// distance rows will be (candidates are drawn before the matrix is filled), the survivor list where the metric features
-// were (the scan starts after the fill).
+// per-warp shared memory, byte offsets (all multiples of 16).  One region is used twice: the survivor list lives where the
+// metric features were (the scan starts after the fill).  The rand() ring has its own kilobyte since the draws of the NEXT
+// block are generated while this block's rows are being scanned.
 struct WarpLayout {
 	int rows_cap; // matrix rows: m rounded up to whole 16-row tiles
-	uint32_t texels, rows, q8, cneg, col, feat, misc, total;
+	uint32_t texels, rows, q8, cneg, col, feat, ring, misc, total;
 };
 __host__ __device__ inline WarpLayout warp_layout(int mcap, bool pack16)
 {
@@ -59,9 +62,7 @@ __host__ __device__ inline WarpLayout warp_layout(int mcap, bool pack16)
 	uint32_t o = 0;
 	L.texels = o; o += 64;                                                       // the current block's texels, reduced
 	uint32_t rows = (uint32_t) L.rows_cap * (pack16 ? kPitch16 : kPitch32) * 4;
-	if (rows < kRing * 4)
-		rows = kRing * 4;
-	L.rows = o; o += rows;                                                       // exact distance rows | rand() ring
+	L.rows = o; o += rows;                                                       // exact distance rows
 	L.q8 = o; o += (uint32_t) L.rows_cap * 16;                                   // quantised rows, one byte per texel
 	L.cneg = o; o += (uint32_t) L.rows_cap * 4;                                  // K - row sum of the quantised row
 	L.col = o; o += ((uint32_t) mcap * 4 + 15) & ~15u;                           // candidate colours
@@ -69,6 +70,7 @@ __host__ __device__ inline WarpLayout warp_layout(int mcap, bool pack16)
 	if (feat < kListCap * 4)
 		feat = kListCap * 4;
 	L.feat = o; o += feat;                                                       // metric features | survivor list
+	L.ring = o; o += kRing * 4;                                                  // rand() outputs, indexed by draw number mod kRing
 	L.misc = o; o += 16;
 	L.total = o;
 	return L;
@@ -238,15 +240,17 @@ __device__ const uint32_t kSamplePairs[32] = {0x00001u, 0x00004u, 0x00008u, 0x00
 // Returns (i << 16) | j of the winner in every lane.  rows: exact distance rows (16-bit packed, pitch kPitch16, or 32-bit,
 // pitch kPitch32; all values >= 0, columns >= n zero); q8 / cneg: workspace for 16 * ntile quantised rows; list: kListCap
 // words; cnt: one word, zero on entry and on exit.
-template <bool PACK16>
+// bg(): warp-uniform background work issued once per tile (the kernel advances its rand() stream there: shuffles and
+// multiply-adds whose latency the VABSDIFF4 stream hides, on pipes the tile loop leaves idle)
+template <bool PACK16, class BG>
 __device__ __forceinline__ uint32_t pruned_search(const uint32_t *rows, uint4 *q8, uint32_t *cneg, uint32_t *list, uint32_t *cnt,
-		int m, int lane, int sadj)
+		int m, int lane, int sadj, BG bg)
 {
 	const int ntile = (m + 15) >> 4;
 	const int jj = lane & 15, half = lane >> 4;
 	BestPair best{0xFFFFFFFFu, 0xFFFFFFFFu};
 	{ // 0. sample pairs
-		const uint32_t p = kSamplePairs[lane];
+		const uint32_t p = kSamplePairs[lane]; // (hoisting this load out of the block loop costs a register: a 12-byte spill, +0.3 %)
 		const int i = (int) (p >> 16), j = (int) (p & 0xFFFFu);
 		if (j < m)
 			best.take(exact_pair_sum<PACK16>(rows, i, j), p);
@@ -336,6 +340,7 @@ __device__ __forceinline__ uint32_t pruned_search(const uint32_t *rows, uint4 *q
 		const bool jok0 = j0 < m, jok1 = has1 && j1 < m;
 		const int alast = has1 ? b + 1 : b;
 		for (int a = 0; a <= alast; ++a) {
+			bg();
 			const int i0 = 16 * a + 8 * half;
 			const int thr0 = (int) (rqk0 - tq2), thr1 = (int) (rqk1 - tq2);
 			const uint4 *qi = q8 + i0;
@@ -363,6 +368,7 @@ __device__ __forceinline__ uint32_t pruned_search(const uint32_t *rows, uint4 *q
 		const uint32_t rqk = 2u * kBoundBias - cneg[j]; // K + Rq[j]
 		const bool jok = j < m;
 		for (int a = 0; a <= b; ++a) {
+			bg();
 			const int i0 = 16 * a + 8 * half;
 			const int thr = (int) (rqk - tq2); // survives iff acc >= K + Rq[j] - 2 (T >> s); may be negative
 			const uint4 *qi = q8 + i0;
@@ -466,7 +472,7 @@ struct RcpTable {
 			v[i] = 0xFFFFFFFFu / i;
 	}
 };
-__device__ const RcpTable kRcp{};
+__constant__ RcpTable kRcp = RcpTable(); // the index (a channel's box length) is warp-uniform: one constant-bank read
 
 // x % len for x < 2^31 with rcp = floor((2^32 - 1) / len): one multiply-high, one correction
 __device__ __forceinline__ uint32_t mod_small(uint32_t x, uint32_t len, uint32_t rcp)
@@ -538,7 +544,7 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, int sadj, uint32_t one, c
 	uint32_t *col = reinterpret_cast<uint32_t *>(wbase + L.col);
 	Feat *feat = reinterpret_cast<Feat *>(wbase + L.feat);
 	uint32_t *list = reinterpret_cast<uint32_t *>(wbase + L.feat);
-	uint32_t *ring = reinterpret_cast<uint32_t *>(wbase + L.rows);
+	uint32_t *ring = reinterpret_cast<uint32_t *>(wbase + L.ring);
 	uint32_t *cnt = reinterpret_cast<uint32_t *>(wbase + L.misc);
 
 	// texel rows are fetched one block ahead: lane y < 4 holds row y of the next block
@@ -555,8 +561,27 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, int sadj, uint32_t one, c
 	uint2 result = make_uint2(0u, 0u);
 	__syncwarp();
 
+	// Prefetch (S2TC_PS_PREFETCH, off): all candidates of a block are built before its first search, so from then on the ring
+	// is free for the draws of the NEXT block -- one rand() step per tile, five dependent shuffle + multiply-add pairs whose
+	// latency (this phase was 9 % of the instructions but 15 % of the stall samples, ncu source view r02b) could hide behind
+	// the VABSDIFF4 stream.  Measured on a B200 it costs more than it hides: 9.49 ms against 9.12 ms per 8192^2 slab (the
+	// tile loop is at the ALU pipe's ceiling and pays for every extra test and live register).  The ring must still hold the
+	// next block's first draw when that block starts: at most kRing - kLag ahead.  What did pay was the ring's own kilobyte
+	// (it used to share the rows' memory: a put-back of the latest window and a range test per step): 9.41 -> 9.12 ms.
+	const int draws = kDraws * nrandom;
+	int bi = 0;
+	auto prefetch = [&]() {
+#if S2TC_PS_PREFETCH
+		if (bi + 1 < nb && gen < pos + 2 * draws && gen <= pos + draws + (kRing - kLag)) {
+			win = rl.step31(win);
+			if (lane < kLag)
+				ring[(gen + lane) & (kRing - 1)] = win >> 1;
+			gen += kLag;
+		}
+#endif
+	};
 	int bx = bx0, by = by0;
-	for (int bi = 0; bi < nb; ++bi, pos += kDraws * nrandom) {
+	for (; bi < nb; ++bi, pos += draws) {
 		const int w = min(4, v.width - bx * 4), h = min(4, v.rows - by * 4);
 		if (++bx == v.blocks_w) {
 			bx = 0;
@@ -603,15 +628,13 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, int sadj, uint32_t one, c
 					len[ch] = hi - lo[ch] + 1u;
 					rcp[ch] = kRcp.v[len[ch]];
 				}
-				// the ring shares its memory with the distance rows: the outputs of the latest step (the only ones that can
-				// reach into this block) are put back from the window itself
-				if (gen > pos && lane < kLag)
-					ring[(gen - kLag + lane) & (kRing - 1)] = win >> 1;
+				// ring[d mod kRing] = draw d of the chunk; whatever of this block's draws the previous block's tile loop has
+				// not generated already (prefetch, below) is generated here
 				for (int k0 = 0; k0 < nrandom; k0 += 32) {
 					const int need = pos + min(nrandom, k0 + 32) * kDraws;
 					while (gen < need) {
 						win = rl.step31(win);
-						if (gen + kLag > pos && lane < kLag)
+						if (lane < kLag)
 							ring[(gen + lane) & (kRing - 1)] = win >> 1;
 						gen += kLag;
 					}
@@ -685,7 +708,7 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, int sadj, uint32_t one, c
 				if constexpr (M::kMayBeNegative) // SRGB: sums can wrap negative, no lower bound to prune with
 					cij = scan_tiles<kPack, true, true>(rows, m, lane);
 				else
-					cij = pruned_search<kPack>(rows, q8, cneg, list, cnt, m, lane, sadj);
+					cij = pruned_search<kPack>(rows, q8, cneg, list, cnt, m, lane, sadj, prefetch);
 				c01 = to565(col[cij >> 16]) | (to565(col[cij & 0xFFFFu]) << 16);
 			}
 
@@ -704,7 +727,7 @@ pair_search_kernel(ImageView v, int nrandom, int mcap, int sadj, uint32_t one, c
 					}
 				}
 				__syncwarp();
-				const uint32_t aij = pruned_search<true>(rows, q8, cneg, list, cnt, m, lane, sadj);
+				const uint32_t aij = pruned_search<true>(rows, q8, cneg, list, cnt, m, lane, sadj, prefetch);
 				a01 = (col[aij >> 16] >> 24) | ((col[aij & 0xFFFFu] >> 24) << 8);
 			}
 			__syncwarp();
