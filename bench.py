@@ -300,8 +300,7 @@ def run_texture(args, wl, world, rank, local, dist):
 
     dxt_n, cd_n, nrandom, refine_n, width, height, gen = wl
     st = Settings(DXT[dxt_n], CD[cd_n], nrandom, REFINE[refine_n], DITHER[args.dither])
-    if st.dither == 2 and world > 1:
-        raise SystemExit("bench.py: DITHER_FLOYDSTEINBERG is a whole-image recurrence; it cannot be row-sharded (use --gpus 1)")
+    fs_chain = st.dither == 2 and world > 1   # Floyd-Steinberg shards run as a chain (sharding.floyd_steinberg_sharded): nothing scales
     bs = s2tc_b200.block_bytes(st.dxt)
     abits = {0: 1, 1: 4, 2: 8}[st.dxt]
     bw, bh = (width + 3) // 4, (height + 3) // 4
@@ -344,10 +343,22 @@ def run_texture(args, wl, world, rank, local, dist):
     per_gpu_bytes = (y1 - y0) * width * 4
     flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda") if per_gpu_bytes <= (126 << 20) else None
 
+    def fs_chain_rows(d_rows, w_, h_, a, b, d_out):
+        """DITHER_FLOYDSTEINBERG over the ranks' shards: error rows travel down the ranks by NCCL send / recv (colour pass,
+        then the alpha seed from the last rank to rank 0, then the alpha pass), then every rank encodes its reduced texels"""
+        from s2tc_b200.sharding import floyd_steinberg_sharded
+        reduced = torch.empty((min(4 * b, h_) - 4 * a) * w_, dtype=torch.int32, device="cuda")
+        keep = floyd_steinberg_sharded(enc, dist, d_rows, w_, h_, 4, abits, a, b, rank, world, reduced,
+                                       lambda n: torch.zeros(n, dtype=torch.int32, device="cuda"), stream=stream.cuda_stream)
+        enc.encode_reduced_rows_device(reduced, w_, h_, a, b, d_out, st, cursor0=0, stream=stream.cuda_stream)
+        return keep, reduced
+
     def step_device():
         if flush is not None:
             flush.add_(1)      # rewrite a buffer larger than the L2 between steps
-        if world == 1:
+        if fs_chain:
+            fs_chain_rows(d_src, width, height, row0, row1, d_dst)
+        elif world == 1:
             enc.encode_rows_device(d_src, width, height, 4, 0, bh, d_dst, st, cursor0=0, carry=None, stream=stream.cuda_stream)
         else:   # summary -> all-gather (128 B per rank, NCCL) -> fold -> encode, all on the device, no host sync
             enc.sharded_encode_async(d_src, width, height, 4, row0, row1, d_dst, st, maps_mine[:16],
@@ -355,7 +366,12 @@ def run_texture(args, wl, world, rank, local, dist):
                                      cursor0=0, stream=stream.cuda_stream)
 
     def step_e2e():
-        if world == 1:
+        if fs_chain:           # no pipeline here: the chain is the critical path
+            d_src.copy_(h_src, non_blocking=True)
+            fs_chain_rows(d_src, width, height, row0, row1, d_dst)
+            h_dst.copy_(d_dst, non_blocking=True)
+            stream.synchronize()
+        elif world == 1:
             enc.compress(h_src, st, cursor=0, out=h_dst)   # the reference-facing host call, pinned buffers
         else:               # striped shards: one 128-byte all-gather per wave, uploads / kernels / downloads overlap
             enc.compress_striped(src_stripes, width, height, dst_stripes, st, rank, world, NWAVE, maps_mine, maps_all,
@@ -397,9 +413,23 @@ def run_texture(args, wl, world, rank, local, dist):
         if st.dither == 2:
             # Floyd-Steinberg: the alpha pass of the reference is seeded from the LAST image row, so a
             # cropped image is not a prefix of the full one; check a smaller whole image through the same code path
-            small = np.ascontiguousarray(img[:256, :256])
-            ok = np.array_equal(enc.compress(small, st), O.orc_compress(small, st.dxt, st.cd, st.nrandom, st.refine, st.dither))
-            checked = 64 * 64
+            small = np.ascontiguousarray(img[:64 * world + 4, :256])
+            want = O.orc_compress(small, st.dxt, st.cd, st.nrandom, st.refine, st.dither)
+            if fs_chain:       # the same chain on the small image; rank 0 compares everybody's rows
+                sbh = (small.shape[0] + 3) // 4
+                a, b = (sbh * rank) // world, (sbh * (rank + 1)) // world
+                d_small = torch.from_numpy(np.ascontiguousarray(small[4 * a:4 * b])).cuda()
+                d_sout = torch.zeros((sbh // world + 1) * 64 * bs, dtype=torch.uint8, device="cuda")
+                fs_chain_rows(d_small, 256, small.shape[0], a, b, d_sout)
+                stream.synchronize()
+                outs = [torch.zeros_like(d_sout) for _ in range(world)]
+                dist.all_gather(outs, d_sout)
+                got_small = np.concatenate([outs[r][:((sbh * (r + 1)) // world - (sbh * r) // world) * 64 * bs].cpu().numpy()
+                                            for r in range(world)])
+                ok = np.array_equal(got_small, want)
+            else:
+                ok = np.array_equal(enc.compress(small, st), want)
+            checked = want.size // bs
         else:
             nrows = max(1, min(my_rows, (16384 if nrandom > 0 else 32768) // bw // 2))
             spans = [(row0, row0 + nrows)] if my_rows <= 2 * nrows else [(row0, row0 + nrows), (row1 - nrows, row1)]
@@ -410,7 +440,7 @@ def run_texture(args, wl, world, rank, local, dist):
                 checked += (b - a) * bw
         step_e2e()     # and the host path must give the same bytes as the device path
         torch.cuda.synchronize()
-        if world == 1:
+        if world == 1 or fs_chain:
             ok = ok and np.array_equal(h_dst[:my_blocks * bs].numpy(), got_dev)
         else:          # the ranks own different rows in the two paths: compare checksums over all block rows of the image
             sums = torch.tensor([row_checksum(got_dev, [(row0, row1)]), row_checksum(hs_dst.numpy(), stripes)], dtype=torch.int64,
@@ -620,6 +650,8 @@ def run_texture(args, wl, world, rank, local, dist):
         "e2e": {"value": e2e_value, "unit": "Mblocks/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": width * height * 4,
                 "d2h_bytes_per_step": total_blocks * bs,
                 "path": "s2tc_b200_compress_host (what tx_compress_dxtn calls), pinned host buffers" if world == 1
+                else "upload, Floyd-Steinberg chain over the ranks (s2tc_b200_floyd_rows_device, NCCL send / recv of the error rows), "
+                     "encode, download: the chain is the critical path, nothing overlaps" if fs_chain
                 else f"s2tc_b200_compress_host_striped per rank: {NWAVE} waves (sizes {WAVES}) x {world} stripes of block rows, stripe w * world + rank "
                      "on rank `rank`; wave w is encoded while wave w + 1 is uploaded; one 128-byte all-gather of DITHER_SIMPLE "
                      "summaries per wave (NCCL); pinned host buffers",
