@@ -20,7 +20,8 @@
 //
 // History of this kernel on config 3 (16.7 M DXT1 blocks, WAVG, nrandom = 64): 198 ms (32-bit rows) -> 52.1 ms (round 1:
 // exact scan in 16x16 tiles, 8 VIMNMX.U16x2 + 8 IDP.2A per pair, 90 % issue utilisation, + 5.3 ms for a separate
-// candidate kernel) -> this version.
+// candidate kernel) -> 39.2 ms (pruned scan, candidates generated here) -> 36.7 ms (survivor groups, the rand() ring in
+// its own memory); the steps and what measured slower are in DESIGN.md 5.1.
 #define S2TC_USE_SRGB_MIXED_LUT
 #include "kernels.cuh"
 
@@ -179,9 +180,11 @@ template <> struct RowRegs<false> {
 //   2. 16x16 tiles: lane (jj, half) keeps the q row j = 16b + jj in registers and meets the eight rows i = 16a + 8 half + t
 //      (broadcast loads).  acc = c[i] + SAD(q[i], q[j]) = K + Rq[j] - 2 bound, so the pair survives iff
 //      acc >= K + Rq[j] - 2 (T >> s), a per-lane constant: one test per four pairs on their maximum;
-//   3. survivors (rare) are appended to a list; when 32 are waiting, or at the end of a tile column, the warp evaluates
-//      them exactly, one per lane, from the full-precision rows and agrees on the new (T, i, j).
-// Diagonal tiles go through the same loop (slots with i >= j are discarded when they try to enter the list); rows
+//   3. surviving GROUPS of four pairs (i .. i+3, j) -- the unit of the test -- are appended to a list (rare); when 32
+//      pairs are waiting, or at the end of a tile column, the warp sums them exactly, one pair per lane, from the
+//      full-precision rows and agrees on the new (T, i, j).
+// Diagonal tiles go through the same loop (groups that start at i >= j never enter the list, pairs with i >= j are
+// skipped at the flush); rows
 // beyond m are all-255 (bound = Rq[i], never better than a real pair of row i).
 // Measured on a B200 (tools_lab/ubench_sad.cu): VABSDIFF4 issues every other clock per scheduler on the ALU pipe,
 // so the bound costs ~10 clocks per pair against ~21 for the exact form, and the other pipes stay free for the rest.
