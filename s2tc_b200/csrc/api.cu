@@ -782,8 +782,9 @@ int compress_rows_host(s2tc_b200_ctx *c, const s2tc_b200_settings &s, int comps,
 	int first_rows = 0, cap_rows = 0;
 	if (s.nrandom > 0 && !exchange && nslab > 1 && !getenv("S2TC_B200_SLAB_MB")) {
 		const size_t row_in = (size_t) width * 4 * comps; // texel bytes per block row
+		static const int cap_mb = [] { const char *e = getenv("S2TC_B200_SLAB_CAP_MB"); int n = e ? atoi(e) : 0; return n >= 16 ? n : 256; }();
 		first_rows = (int) (((size_t) 16 << 20) / row_in);
-		cap_rows = (int) (((size_t) 256 << 20) / row_in);
+		cap_rows = (int) (((size_t) cap_mb << 20) / row_in);
 		if (first_rows < 1 || cap_rows < first_rows) {
 			first_rows = 0;
 		} else {
