@@ -42,6 +42,9 @@ constexpr uint32_t kFlushGroups = 8; // 8 groups = 32 pairs = one exact sum per 
 #ifndef S2TC_PS_MINCTAS
 #define S2TC_PS_MINCTAS 32
 #endif
+#ifndef S2TC_PS_DIAG
+#define S2TC_PS_DIAG 1 // diagonal tiles as 4 pairs per lane (circular offsets) instead of 8 rows x 16 columns with half the slots void
+#endif
 #ifndef S2TC_PS_PREFETCH
 #define S2TC_PS_PREFETCH 0 // 1: the next block's rand() draws are generated inside this block's tile loop (measured slower, see pair_search_kernel)
 #endif
@@ -189,6 +192,7 @@ template <> struct RowRegs<false> {
 // Measured on a B200 (tools_lab/ubench_sad.cu): VABSDIFF4 issues every other clock per scheduler on the ALU pipe,
 // so the bound costs ~10 clocks per pair against ~21 for the exact form, and the other pipes stay free for the rest.
 constexpr uint32_t kBoundBias = 4096; // K > 16 * 255
+constexpr uint32_t kDiagGroup = 0x80000000u; // list entry: a group of a diagonal tile (see the flush)
 
 __device__ __forceinline__ uint32_t sad4(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -304,7 +308,7 @@ __device__ __forceinline__ uint32_t pruned_search(const uint32_t *rows, uint4 *q
 	uint32_t tq2 = (best.sum >> s) * 2u;
 	bool pending = false; // this lane has appended since the list was last emptied
 	auto append = [&](uint32_t top, int thr, bool jok, int ig, int j) {
-		if ((int) top >= thr && jok && ig < j) {
+		if ((int) top >= thr && jok && ((S2TC_PS_DIAG && !S2TC_PS_TWOCOL) || ig < j)) { // (tiles below the diagonal: every i < j)
 			list[atomicAdd(cnt, 1u)] = ((uint32_t) ig << 16) | (uint32_t) j;
 			pending = true;
 		}
@@ -321,10 +325,14 @@ __device__ __forceinline__ uint32_t pruned_search(const uint32_t *rows, uint4 *q
 				if (lane == 0)
 					*cnt = 0;
 				for (uint32_t idx = lane; idx < 4u * c; idx += 32) {
-					const uint32_t p = list[idx >> 2] + ((idx & 3u) << 16);
-					const int i = (int) (p >> 16), j = (int) (p & 0xFFFFu);
-					if (i < j)
-						best.take(exact_pair_sum<PACK16>(rows, i, j), p);
+					const uint32_t e = list[idx >> 2], t = idx & 3u;
+					const uint32_t base = (e >> 16) & 0x7FFFu;
+					// ordinary group: rows base .. base + 3; diagonal-tile group (flag): rows base .. base + 3 inside the
+					// tile's 16 rows, wrapping around
+					const int i = (e & kDiagGroup) ? (int) ((base & ~15u) | ((base + t) & 15u)) : (int) (base + t), j = (int) (e & 0xFFFFu);
+					const int lo = min(i, j), hi = max(i, j);
+					if (lo < hi && hi < m)
+						best.take(exact_pair_sum<PACK16>(rows, lo, hi), ((uint32_t) lo << 16) | (uint32_t) hi);
 				}
 				best.warp_min();
 				tq2 = (best.sum >> s) * 2u;
@@ -370,7 +378,12 @@ __device__ __forceinline__ uint32_t pruned_search(const uint32_t *rows, uint4 *q
 		const uint4 rj = q8[j];
 		const uint32_t rqk = 2u * kBoundBias - cneg[j]; // K + Rq[j]
 		const bool jok = j < m;
-		for (int a = 0; a <= b; ++a) {
+#if S2TC_PS_DIAG
+		const int atop = b; // tiles a < b in full; the diagonal tile below
+#else
+		const int atop = b + 1;
+#endif
+		for (int a = 0; a < atop; ++a) {
 			bg();
 			const int i0 = 16 * a + 8 * half;
 			const int thr = (int) (rqk - tq2); // survives iff acc >= K + Rq[j] - 2 (T >> s); may be negative
@@ -390,6 +403,30 @@ __device__ __forceinline__ uint32_t pruned_search(const uint32_t *rows, uint4 *q
 				append(max(max(acc[g], acc[g + 1]), max(acc[g + 2], acc[g + 3])), thr, jok, i0 + g, j);
 			flush_if(a == b, a == b && (b == 0 || b == ntile - 1));
 		}
+#if S2TC_PS_DIAG
+		{ // The diagonal tile: 120 pairs among 16 rows.  In the 8 x 16 shape above half of the slots hold i >= j.  Instead lane
+		  // (jj, half) meets the four rows at circular offsets 1 + 4 half .. 4 + 4 half from its own row j: every unordered
+		  // pair is met once (circular distance 1..7) or twice (distance 8: the same exact sum twice, harmless) -- 16 VABSDIFF4
+		  // per lane instead of 32.  The partner rows differ per lane (plain loads, not broadcasts); rows beyond m are
+		  // filtered at the flush.
+			bg();
+			const int thr = (int) (rqk - tq2);
+			const uint32_t o0 = (uint32_t) (jj + 1 + 4 * half);
+			const int tb = 16 * b;
+			uint32_t acc[4];
+#pragma unroll
+			for (int t = 0; t < 4; ++t) {
+				const int i = tb + (int) ((o0 + t) & 15u);
+				acc[t] = sad_row(q8[i], rj, cneg[i]);
+			}
+			const uint32_t top = max(max(acc[0], acc[1]), max(acc[2], acc[3]));
+			if ((int) top >= thr && jok) {
+				list[atomicAdd(cnt, 1u)] = kDiagGroup | ((uint32_t) (tb + (int) (o0 & 15u)) << 16) | (uint32_t) j;
+				pending = true;
+			}
+			flush_if(true, b == 0 || b == ntile - 1);
+		}
+#endif
 	}
 #endif
 	__syncwarp();
