@@ -21,7 +21,7 @@
 // History of this kernel on config 3 (16.7 M DXT1 blocks, WAVG, nrandom = 64): 198 ms (32-bit rows) -> 52.1 ms (round 1:
 // exact scan in 16x16 tiles, 8 VIMNMX.U16x2 + 8 IDP.2A per pair, 90 % issue utilisation, + 5.3 ms for a separate
 // candidate kernel) -> 39.2 ms (pruned scan, candidates generated here) -> 36.7 ms (survivor groups, the rand() ring in
-// its own memory); the steps and what measured slower are in DESIGN.md 5.1.
+// its own memory) -> 33.9 ms (diagonal tiles as 4 pairs per lane); the steps and what measured slower are in DESIGN.md 5.1.
 #define S2TC_USE_SRGB_MIXED_LUT
 #include "kernels.cuh"
 
