@@ -42,6 +42,9 @@ constexpr uint32_t kFlushGroups = 8; // 8 groups = 32 pairs = one exact sum per 
 #ifndef S2TC_PS_MINCTAS
 #define S2TC_PS_MINCTAS 32
 #endif
+#ifndef S2TC_PS_MINFLUSH
+#define S2TC_PS_MINFLUSH 1 // groups that must be waiting for a flush at a column end that is not the last one
+#endif
 #ifndef S2TC_PS_DIAG
 #define S2TC_PS_DIAG 1 // diagonal tiles as 4 pairs per lane (circular offsets) instead of 8 rows x 16 columns with half the slots void
 #endif
@@ -319,7 +322,7 @@ __device__ __forceinline__ uint32_t pruned_search(const uint32_t *rows, uint4 *q
 			const uint32_t c = *cnt;
 			// S2TC_PS_FLUSH 0: at every column end (T as fresh as possible); 1: after the first column, at the end, and
 			// whenever 32 pairs are waiting
-			const bool now = c >= kFlushGroups || (S2TC_PS_FLUSH == 0 ? last_of_column : last_of_all);
+			const bool now = c >= kFlushGroups || last_of_all || (S2TC_PS_FLUSH == 0 && last_of_column && c >= S2TC_PS_MINFLUSH);
 			if (now) {
 				__syncwarp(); // every lane has read the count
 				if (lane == 0)
